@@ -1,0 +1,100 @@
+"""Build libai_b200.so (the C-ABI library of include/ai_b200.h) in-tree with nvcc for sm_100a.
+
+    python -m adaptive_interpolation_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  The product is adaptive_interpolation_b200/_lib/libai_b200.so
+(git-ignored; it travels to the GPU box with the working tree).  Replaces the reference's
+per-approximation `ispc` + `g++ -shared` build at run_test.py:46-122,190-218: ONE library, built
+once, serves every table.
+"""
+import concurrent.futures
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "_lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libai_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--ftz=false", "--prec-div=true", "--prec-sqrt=true", "--fmad=true",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(ROOT, "include", "ai_b200.h"))
+    return sorted(hs)
+
+
+def fingerprint():
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for path in sources() + headers():
+        h.update(path.encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def is_current():
+    stamp = os.path.join(LIBDIR, "fingerprint")
+    if not (os.path.exists(LIB) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as fh:
+        return fh.read().strip() == fingerprint()
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA translation unit for sm_100a and link the shared library."""
+    if not force and is_current():
+        return LIB
+    nvcc = nvcc_path()
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        return obj, r.stderr
+
+    workers = max(1, min(len(sources()), os.cpu_count() or 1))
+    with concurrent.futures.ThreadPoolExecutor(workers) as ex:
+        results = list(ex.map(compile_one, sources()))
+    objs = [o for o, _ in results]
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(os.path.join(LIBDIR, "fingerprint"), "w") as fh:
+        fh.write(fingerprint())
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,726 @@
+// ai_api.cu -- the C ABI of include/ai_b200.h: table construction (host), kernel dispatch,
+// the host-buffer pipeline, and the measurement helpers.
+//
+// Reference interfaces replaced (see include/ai_b200.h for the full mapping):
+//   adaptive_interpolation/generate.py:408-502   build_code / run / run_single / run_multi
+//   run_test.py:242-283                          ctypes call of the generated eval(...)
+//   adaptive_interpolation/approximator.py:191-243  tree flattening + uniform-grid map
+#include "../../include/ai_b200.h"
+#include "ai_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define AI_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(AI_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+constexpr int kGridMaxExact = 16384;   // cells allowed when the grid alone resolves the leaf
+constexpr int kGridMaxSearch = 4096;   // cells when a search follows anyway
+
+// Test hook: AI_B200_MAX_CELLS=<n> caps both budgets, forcing the search path on tables whose
+// breakpoints would otherwise sit on cell edges (tests/test_gpu_parity.py).
+int grid_budget(int dflt) {
+    const char* e = std::getenv("AI_B200_MAX_CELLS");
+    if (!e || !*e) return dflt;
+    const long v = std::strtol(e, nullptr, 10);
+    return (v >= 1 && v < dflt) ? (int)v : dflt;
+}
+constexpr int kHostSlots = 3;          // host pipeline depth
+
+struct HostPipe {
+    bool ready = false;
+    int64_t chunk = 0;                 // elements per chunk
+    void* dx[kHostSlots] = {nullptr, nullptr, nullptr};
+    void* dy[kHostSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[kHostSlots], k_done[kHostSlots], out_done[kHostSlots];
+    cudaEvent_t k_start[kHostSlots];
+    std::mutex mu;
+};
+
+}  // namespace
+
+struct ai_table {
+    int basis = 0, order = 0, dtype = 0, device = 0;
+    int64_t L = 0;
+    int G = 0, p = 0, K = 0;
+    long long g0 = 0;
+    int rstride = 0;
+    std::vector<double> breaks;        // L+1, exact widening of the table dtype
+    std::vector<double> coef;          // L*(order+1)
+    void* d_image = nullptr;
+    ai::TableView view{};
+    int blocks_per_sm = 1, sm_count = 1;
+    int smem_resident = 1;
+    HostPipe pipe;
+};
+
+namespace {
+
+// Build the exact power-of-two grid for sorted breakpoints b[0..L].
+//   cell(x) = floor(x * 2^p);  first[g] = leaf holding the left edge of cell g0+g.
+// K = 0 when every interior breakpoint is a cell edge (then first[] alone is the answer).
+struct GridPlan {
+    int p = 0, K = 0, G = 0;
+    long long g0 = 0;
+    std::vector<uint16_t> first;
+};
+
+bool cells_for(const std::vector<double>& b, int p, long long* g0, long long* glast) {
+    const double lo = std::ldexp(b.front(), p), hi = std::ldexp(b.back(), p);
+    if (!(std::fabs(lo) < 9.0e15) || !(std::fabs(hi) < 9.0e15)) return false;
+    *g0 = (long long)std::floor(lo);
+    long long gl = (long long)std::ceil(hi) - 1;     // last cell holding a point < ub
+    if (gl < *g0) gl = *g0;
+    *glast = gl;
+    return true;
+}
+
+int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
+    const int64_t L = (int64_t)b.size() - 1;
+    const long long rep_limit = (dtype == AI_DTYPE_F32) ? (1LL << 24) : (1LL << 30);
+    auto fits = [&](int p, int gmax, long long* g0, long long* gl) {
+        if (!cells_for(b, p, g0, gl)) return false;
+        if (*gl - *g0 + 1 > gmax) return false;
+        return std::llabs(*g0) < rep_limit && std::llabs(*gl) < rep_limit;
+    };
+    // smallest p >= 0 at which all interior breakpoints are integers after scaling
+    int p_exact = -1;
+    for (int p = 0; p <= 60; ++p) {
+        bool all = true;
+        for (int64_t k = 1; k < L && all; ++k) {
+            const double v = std::ldexp(b[k], p);
+            all = (std::fabs(v) < 9.0e15) && (v == std::floor(v));
+        }
+        if (all) { p_exact = p; break; }
+    }
+    long long g0 = 0, gl = 0;
+    int p = 0;
+    bool exact = false;
+    if (p_exact >= 0 && fits(p_exact, grid_budget(kGridMaxExact), &g0, &gl)) {
+        p = p_exact;
+        exact = true;
+    } else {
+        // finest grid within the budget; p may be negative for very wide domains
+        bool found = false;
+        for (int q = 60; q >= -1000; --q) {
+            if (fits(q, grid_budget(kGridMaxSearch), &g0, &gl)) { p = q; found = true; break; }
+        }
+        if (!found) return fail(AI_ERR_TABLE, "cannot build a lookup grid for domain [%g, %g]", b.front(), b.back());
+    }
+    const int G = (int)(gl - g0 + 1);
+    out->p = p; out->G = G; out->g0 = g0;
+    out->first.assign(G, 0);
+    // A negative p scales DOWN and can underflow for denormal-range x; widen the search window
+    // by one cell to the left so the result stays exact regardless.
+    const int margin = (p < 0) ? 1 : 0;
+    int64_t maxspan = 0;
+    for (int g = 0; g < G; ++g) {
+        const double left = std::ldexp((double)(g0 + g - margin), -p);
+        const double right = std::ldexp((double)(g0 + g + 1), -p);
+        // leaf holding `left`: #{k: b[k] <= left} - 1, clamped
+        int64_t f = (std::upper_bound(b.begin(), b.end(), left) - b.begin()) - 1;
+        f = std::min<int64_t>(std::max<int64_t>(f, 0), L - 1);
+        // last leaf with a point < right
+        int64_t l = (std::lower_bound(b.begin(), b.end(), right) - b.begin()) - 1;
+        l = std::min<int64_t>(std::max<int64_t>(l, 0), L - 1);
+        if (g == G - 1) l = L - 1;
+        if (g == 0) f = 0;
+        out->first[g] = (uint16_t)f;
+        maxspan = std::max(maxspan, l - f);
+    }
+    int K = 0;
+    while ((1LL << K) - 1 < maxspan) ++K;
+    if (exact && K != 0) return fail(AI_ERR_TABLE, "internal: exact grid has span %lld", (long long)maxspan);
+    out->K = K;
+    return AI_OK;
+}
+
+int round_up16(size_t v) { return (int)((v + 15) & ~(size_t)15); }
+
+template <typename T>
+int build_image(ai_table* t, const GridPlan& gp, std::vector<unsigned char>* image) {
+    const int n = t->order;
+    const int64_t L = t->L;
+    const int R = ai::rec_stride(t->basis, n);
+    const int hdr = (t->basis == ai::kMono) ? 0 : 2;
+    const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
+    const int off_first = 0;
+    const int off_breaks = round_up16((size_t)gp.G * sizeof(uint16_t));
+    const int off_records = off_breaks + round_up16((size_t)(L + 1 + pad) * sizeof(T));
+    const size_t total = (size_t)off_records + (size_t)round_up16((size_t)L * R * sizeof(T));
+    image->assign(total, 0);
+    std::memcpy(image->data() + off_first, gp.first.data(), gp.first.size() * sizeof(uint16_t));
+    T* br = reinterpret_cast<T*>(image->data() + off_breaks);
+    for (int64_t k = 0; k <= L; ++k) br[k] = (T)t->breaks[k];
+    for (int k = 0; k < pad; ++k) br[L + 1 + k] = std::numeric_limits<T>::infinity();
+    T* rec = reinterpret_cast<T*>(image->data() + off_records);
+    for (int64_t i = 0; i < L; ++i) {
+        T* r = rec + i * R;
+        if (hdr) {
+            const T a = (T)t->breaks[i], b = (T)t->breaks[i + 1];
+            r[0] = a;
+            r[1] = (T)2 / (b - a);       // in T arithmetic: generate.py:83 `(2./(b - a))`
+        }
+        for (int j = 0; j <= n; ++j) r[hdr + j] = (T)t->coef[i * (n + 1) + j];
+    }
+    t->rstride = R;
+    t->view.image_bytes = (int)total;
+    t->view.off_first = off_first;
+    t->view.off_breaks = off_breaks;
+    t->view.off_records = off_records;
+    return AI_OK;
+}
+
+int prepare_dispatch(int basis, int dtype, int order, int smem, int* bps) {
+    cudaError_t e = cudaErrorInvalidValue;
+    if (dtype == AI_DTYPE_F32) {
+        if (basis == ai::kCheb) e = ai::prepare_cheb_f32(order, smem, bps);
+        else if (basis == ai::kLeg) e = ai::prepare_leg_f32(order, smem, bps);
+        else e = ai::prepare_mono_f32(order, smem, bps);
+    } else {
+        if (basis == ai::kCheb) e = ai::prepare_cheb_f64(order, smem, bps);
+        else if (basis == ai::kLeg) e = ai::prepare_leg_f64(order, smem, bps);
+        else e = ai::prepare_mono_f64(order, smem, bps);
+    }
+    if (e != cudaSuccess) return fail(AI_ERR_CUDA, "kernel prepare failed: %s", cudaGetErrorString(e));
+    return AI_OK;
+}
+
+int finish_table(ai_table* t) {
+    // validate the flattened table
+    const int64_t L = t->L;
+    for (int64_t k = 0; k <= L; ++k)
+        if (!std::isfinite(t->breaks[k])) return fail(AI_ERR_TABLE, "breakpoint %lld is not finite", (long long)k);
+    for (int64_t k = 0; k < L; ++k)
+        if (!(t->breaks[k] < t->breaks[k + 1]))
+            return fail(AI_ERR_TABLE, "breakpoints not strictly increasing at %lld (%.17g, %.17g)",
+                        (long long)k, t->breaks[k], t->breaks[k + 1]);
+    if (L > 65535) return fail(AI_ERR_UNSUPPORTED, "more than 65535 leaves (%lld) not supported yet", (long long)L);
+
+    GridPlan gp;
+    int rc = plan_grid(t->breaks, t->dtype, &gp);
+    if (rc) return rc;
+    t->G = gp.G; t->p = gp.p; t->K = gp.K; t->g0 = gp.g0;
+
+    std::vector<unsigned char> image;
+    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, &image) : build_image<double>(t, gp, &image);
+    if (rc) return rc;
+
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
+    cudaDeviceProp prop;
+    AI_CUDA(cudaGetDeviceProperties(&prop, t->device));
+    if (prop.major < 10)
+        return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    t->device, prop.major, prop.minor);
+    t->sm_count = prop.multiProcessorCount;
+    if ((size_t)t->view.image_bytes > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(AI_ERR_UNSUPPORTED, "table image (%d B) exceeds shared memory per CTA (%zu B); "
+                    "the L2-resident path is not built yet", t->view.image_bytes, (size_t)prop.sharedMemPerBlockOptin);
+    AI_CUDA(cudaMalloc(&t->d_image, image.size()));
+    AI_CUDA(cudaMemcpy(t->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
+
+    t->view.image = static_cast<const unsigned char*>(t->d_image);
+    t->view.n_leaves = (int)L;
+    t->view.g0 = (int)gp.g0;
+    t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
+    t->view.scale = std::ldexp(1.0, gp.p);
+    t->view.lo = (double)gp.g0;
+    t->view.hi = (double)(gp.g0 + gp.G - 1);
+    // adapt.py:107 `*(1./n)`: 1./n in double, then rounded to the table dtype by the multiply
+    const double inv = t->order > 0 ? 1.0 / (double)t->order : 0.0;
+    t->view.inv_order = (t->dtype == AI_DTYPE_F32) ? (double)(float)inv : inv;
+
+    int bps = 0;
+    rc = prepare_dispatch(t->basis, t->dtype, t->order, t->view.image_bytes, &bps);
+    if (rc) return rc;
+    if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->view.image_bytes);
+    t->blocks_per_sm = bps;
+    return AI_OK;
+}
+
+int check_common(int basis, int order, int dtype, int device) {
+    if (basis < 0 || basis > 2) return fail(AI_ERR_INVALID, "basis %d not in {0 chebyshev, 1 legendre, 2 monomial}", basis);
+    if (order < 0 || order > AI_MAX_ORDER) return fail(AI_ERR_INVALID, "order %d not in [0, %d]", order, AI_MAX_ORDER);
+    if (dtype != AI_DTYPE_F32 && dtype != AI_DTYPE_F64) return fail(AI_ERR_INVALID, "dtype %d not in {0 f32, 1 f64}", dtype);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail(AI_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(AI_ERR_INVALID, "device %d not in [0, %d)", device, count);
+    return AI_OK;
+}
+
+template <typename T>
+int launch_eval_t(const ai_table* t, const T* x, T* y, int64_t n, cudaStream_t stream) {
+    if (n == 0) return AI_OK;
+    constexpr int VN = ai::Vec<T>::N;
+    const uintptr_t ax = reinterpret_cast<uintptr_t>(x), ay = reinterpret_cast<uintptr_t>(y);
+    if ((ax % sizeof(T)) || (ay % sizeof(T))) return fail(AI_ERR_INVALID, "x / y not aligned to the element size");
+    long long head, nvec;
+    if ((ax % 16) == (ay % 16)) {
+        head = (long long)(((16 - (ax % 16)) % 16) / sizeof(T));
+        if (head > n) head = n;
+        nvec = (n - head) / VN;
+    } else {            // x and y can never be 16-byte aligned together: scalar path
+        head = n;
+        nvec = 0;
+    }
+    ai::LaunchCfg cfg;
+    const long long tile_elems = (long long)ai::kBlock * ai::kUnroll * VN;
+    const long long want = (n + tile_elems - 1) / tile_elems;
+    cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
+    cfg.smem_bytes = t->view.image_bytes;
+    cfg.stream = stream;
+    cudaError_t e;
+    if constexpr (sizeof(T) == 4) {
+        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f32(t->order, cfg, t->view, x, y, n, head, nvec);
+        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f32(t->order, cfg, t->view, x, y, n, head, nvec);
+        else e = ai::launch_eval_mono_f32(t->order, cfg, t->view, x, y, n, head, nvec);
+    } else {
+        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f64(t->order, cfg, t->view, x, y, n, head, nvec);
+        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f64(t->order, cfg, t->view, x, y, n, head, nvec);
+        else e = ai::launch_eval_mono_f64(t->order, cfg, t->view, x, y, n, head, nvec);
+    }
+    if (e != cudaSuccess) return fail(AI_ERR_CUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));
+    return AI_OK;
+}
+
+template <typename T>
+int eval_entry(const ai_table* t, const T* x, T* y, int64_t n, void* stream) {
+    if (!t) return fail(AI_ERR_INVALID, "table handle is NULL");
+    if (n < 0) return fail(AI_ERR_INVALID, "n = %lld is negative", (long long)n);
+    if ((sizeof(T) == 4) != (t->dtype == AI_DTYPE_F32))
+        return fail(AI_ERR_DTYPE, "table dtype is %s but the %s entry point was called",
+                    t->dtype == AI_DTYPE_F32 ? "f32" : "f64", sizeof(T) == 4 ? "f32" : "f64");
+    if (n > 0 && (!x || !y)) return fail(AI_ERR_INVALID, "x or y is NULL");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
+    return launch_eval_t<T>(t, x, y, n, static_cast<cudaStream_t>(stream));
+}
+
+template <typename T>
+int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* stream) {
+    if (!t) return fail(AI_ERR_INVALID, "table handle is NULL");
+    if (n < 0) return fail(AI_ERR_INVALID, "n = %lld is negative", (long long)n);
+    if ((sizeof(T) == 4) != (t->dtype == AI_DTYPE_F32)) return fail(AI_ERR_DTYPE, "table dtype mismatch");
+    if (n == 0) return AI_OK;
+    if (!x || !idx) return fail(AI_ERR_INVALID, "x or idx is NULL");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
+    if (t->view.image_bytes > 48 * 1024)
+        AI_CUDA(cudaFuncSetAttribute(ai::index_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->view.image_bytes));
+    const long long want = (n + ai::kBlock - 1) / ai::kBlock;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * 4));
+    ai::index_kernel<T><<<grid, ai::kBlock, t->view.image_bytes, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
+    AI_CUDA(cudaGetLastError());
+    return AI_OK;
+}
+
+template <typename T>
+int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* stream) {
+    if (!t) return fail(AI_ERR_INVALID, "table handle is NULL");
+    if (n < 0) return fail(AI_ERR_INVALID, "n = %lld is negative", (long long)n);
+    if ((sizeof(T) == 4) != (t->dtype == AI_DTYPE_F32)) return fail(AI_ERR_DTYPE, "table dtype mismatch");
+    if (!result || (n > 0 && !x)) return fail(AI_ERR_INVALID, "x or result is NULL");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AI_CUDA(cudaMemsetAsync(result, 0, sizeof(double), s));
+    if (n == 0) return AI_OK;
+    ai::LaunchCfg cfg;
+    const long long want = (n + ai::kBlock - 1) / ai::kBlock;
+    cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
+    cfg.smem_bytes = t->view.image_bytes;
+    cfg.stream = s;
+    cudaError_t e;
+    if constexpr (sizeof(T) == 4) {
+        if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, cfg, t->view, x, result, n);
+        else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, cfg, t->view, x, result, n);
+        else e = ai::launch_sum_mono_f32(t->order, cfg, t->view, x, result, n);
+    } else {
+        if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f64(t->order, cfg, t->view, x, result, n);
+        else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f64(t->order, cfg, t->view, x, result, n);
+        else e = ai::launch_sum_mono_f64(t->order, cfg, t->view, x, result, n);
+    }
+    if (e != cudaSuccess) return fail(AI_ERR_CUDA, "sum kernel launch failed: %s", cudaGetErrorString(e));
+    return AI_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer pipeline
+int pipe_init(ai_table* t, size_t elem) {
+    HostPipe& p = t->pipe;
+    if (p.ready) return AI_OK;
+    p.chunk = (int64_t)(32u << 20) / (int64_t)elem;          // 32 MiB per direction per slot
+    for (int s = 0; s < kHostSlots; ++s) {
+        AI_CUDA(cudaMalloc(&p.dx[s], (size_t)p.chunk * elem));
+        AI_CUDA(cudaMalloc(&p.dy[s], (size_t)p.chunk * elem));
+        AI_CUDA(cudaEventCreateWithFlags(&p.in_done[s], cudaEventDisableTiming));
+        AI_CUDA(cudaEventCreateWithFlags(&p.out_done[s], cudaEventDisableTiming));
+        AI_CUDA(cudaEventCreate(&p.k_start[s]));
+        AI_CUDA(cudaEventCreate(&p.k_done[s]));
+    }
+    AI_CUDA(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+    AI_CUDA(cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking));
+    AI_CUDA(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+    p.ready = true;
+    return AI_OK;
+}
+
+void pipe_destroy(ai_table* t) {
+    HostPipe& p = t->pipe;
+    if (!p.ready) return;
+    for (int s = 0; s < kHostSlots; ++s) {
+        cudaFree(p.dx[s]); cudaFree(p.dy[s]);
+        cudaEventDestroy(p.in_done[s]); cudaEventDestroy(p.out_done[s]);
+        cudaEventDestroy(p.k_start[s]); cudaEventDestroy(p.k_done[s]);
+    }
+    cudaStreamDestroy(p.s_in); cudaStreamDestroy(p.s_k); cudaStreamDestroy(p.s_out);
+    p.ready = false;
+}
+
+template <typename T>
+int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_ms) {
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (!ct) return fail(AI_ERR_INVALID, "table handle is NULL");
+    if (n < 0) return fail(AI_ERR_INVALID, "n = %lld is negative", (long long)n);
+    if ((sizeof(T) == 4) != (ct->dtype == AI_DTYPE_F32)) return fail(AI_ERR_DTYPE, "table dtype mismatch");
+    if (n == 0) return AI_OK;
+    if (!x || !y) return fail(AI_ERR_INVALID, "x or y is NULL");
+    ai_table* t = const_cast<ai_table*>(ct);          // the pipeline scratch is mutable state
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
+    std::lock_guard<std::mutex> lock(t->pipe.mu);
+    int rc = pipe_init(t, sizeof(T));
+    if (rc) return rc;
+    HostPipe& p = t->pipe;
+    const int64_t nchunks = (n + p.chunk - 1) / p.chunk;
+    double ms_total = 0.0;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % kHostSlots);
+        const int64_t off = c * p.chunk, m = std::min<int64_t>(p.chunk, n - off);
+        if (c >= kHostSlots) {
+            // slot reuse: its previous D2H must have drained before we overwrite dx/dy
+            AI_CUDA(cudaEventSynchronize(p.out_done[s]));
+            float ms = 0.f;
+            AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
+            ms_total += ms;
+        }
+        AI_CUDA(cudaMemcpyAsync(p.dx[s], x + off, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, p.s_in));
+        AI_CUDA(cudaEventRecord(p.in_done[s], p.s_in));
+        AI_CUDA(cudaStreamWaitEvent(p.s_k, p.in_done[s], 0));
+        AI_CUDA(cudaEventRecord(p.k_start[s], p.s_k));
+        rc = launch_eval_t<T>(t, static_cast<const T*>(p.dx[s]), static_cast<T*>(p.dy[s]), m, p.s_k);
+        if (rc) return rc;
+        AI_CUDA(cudaEventRecord(p.k_done[s], p.s_k));
+        AI_CUDA(cudaStreamWaitEvent(p.s_out, p.k_done[s], 0));
+        AI_CUDA(cudaMemcpyAsync(y + off, p.dy[s], (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, p.s_out));
+        AI_CUDA(cudaEventRecord(p.out_done[s], p.s_out));
+    }
+    AI_CUDA(cudaStreamSynchronize(p.s_out));
+    const int64_t first_pending = std::max<int64_t>(0, nchunks - kHostSlots);
+    for (int64_t c = first_pending; c < nchunks; ++c) {
+        const int s = (int)(c % kHostSlots);
+        float ms = 0.f;
+        AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
+        ms_total += ms;
+    }
+    if (kernel_ms) *kernel_ms = ms_total;
+    return AI_OK;
+}
+
+// ------------------------------------------------------------------ measurement kernels
+template <typename T>
+__global__ void __launch_bounds__(256) fma_chain_kernel(T* out, int iters, T a, T b) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (T)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ai::fma_(v[k], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == (T)123456789) out[0] = s;      // never true; keeps the chain alive
+}
+
+template <typename V>
+__global__ void __launch_bounds__(ai::kBlock) copy_kernel(const V* __restrict__ x, V* __restrict__ y, long long nvec) {
+    constexpr long long kTile = (long long)ai::kBlock * ai::kUnroll;
+    const long long full = nvec / kTile;
+    for (long long tile = blockIdx.x; tile < full; tile += gridDim.x) {
+        const long long base = tile * kTile + threadIdx.x;
+        V in[ai::kUnroll];
+#pragma unroll
+        for (int u = 0; u < ai::kUnroll; ++u) in[u] = __ldcs(x + base + (long long)u * ai::kBlock);
+#pragma unroll
+        for (int u = 0; u < ai::kUnroll; ++u) __stcs(y + base + (long long)u * ai::kBlock, in[u]);
+    }
+    for (long long v = full * kTile + (long long)blockIdx.x * ai::kBlock + threadIdx.x; v < nvec;
+         v += (long long)gridDim.x * ai::kBlock)
+        __stcs(y + v, __ldcs(x + v));
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+const char* ai_last_error(void) { return g_err.c_str(); }
+const char* ai_version(void) { return "ai_b200 0.1.0 sm_100a"; }
+
+int ai_device_count(int* count) {
+    if (!count) return fail(AI_ERR_INVALID, "count is NULL");
+    AI_CUDA(cudaGetDeviceCount(count));
+    return AI_OK;
+}
+
+int ai_device_sm_arch(int device, int* major, int* minor, int* sm_count) {
+    cudaDeviceProp prop;
+    AI_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (major) *major = prop.major;
+    if (minor) *minor = prop.minor;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return AI_OK;
+}
+
+int ai_table_create(int basis, int order, int dtype, int64_t n_leaves, const void* breaks,
+                    const void* coef, int device, ai_table_t** out) {
+    if (!out) return fail(AI_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_common(basis, order, dtype, device);
+    if (rc) return rc;
+    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
+    if (!breaks || !coef) return fail(AI_ERR_INVALID, "breaks or coef is NULL");
+    ai_table* t = new ai_table;
+    t->basis = basis; t->order = order; t->dtype = dtype; t->device = device; t->L = n_leaves;
+    t->breaks.resize(n_leaves + 1);
+    t->coef.resize((size_t)n_leaves * (order + 1));
+    if (dtype == AI_DTYPE_F32) {
+        const float* b = static_cast<const float*>(breaks);
+        const float* c = static_cast<const float*>(coef);
+        for (int64_t k = 0; k <= n_leaves; ++k) t->breaks[k] = b[k];
+        for (size_t k = 0; k < t->coef.size(); ++k) t->coef[k] = c[k];
+    } else {
+        const double* b = static_cast<const double*>(breaks);
+        const double* c = static_cast<const double*>(coef);
+        for (int64_t k = 0; k <= n_leaves; ++k) t->breaks[k] = b[k];
+        for (size_t k = 0; k < t->coef.size(); ++k) t->coef[k] = c[k];
+    }
+    rc = finish_table(t);
+    if (rc) { ai_table_destroy(t); return rc; }
+    *out = t;
+    return AI_OK;
+}
+
+int ai_table_create_from_tree(int basis, int order, int dtype, int num_levels, int layout,
+                              const void* tree_1d, int64_t n_elems, int device, ai_table_t** out) {
+    if (!out) return fail(AI_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_common(basis, order, dtype, device);
+    if (rc) return rc;
+    if (!tree_1d || n_elems <= 0) return fail(AI_ERR_INVALID, "tree_1d is NULL or empty");
+    if (layout != AI_TREE_LAYOUT_STANDARD && layout != AI_TREE_LAYOUT_TRIM)
+        return fail(AI_ERR_INVALID, "unknown tree layout %d", layout);
+    if (num_levels < 1) return fail(AI_ERR_INVALID, "num_levels %d < 1", num_levels);
+    auto at = [&](int64_t k) -> double {
+        return dtype == AI_DTYPE_F32 ? (double)static_cast<const float*>(tree_1d)[k]
+                                     : static_cast<const double*>(tree_1d)[k];
+    };
+    const int n = order;
+    std::vector<double> a, b, coef;
+    // Iterative in-order traversal over element offsets, following the child links the way
+    // Approximator.evaluate does (approximator.py:274-290).  Standard layout: children are
+    // ELEMENT offsets at [n+4], [n+5], leaves point to themselves (approximator.py:198-199).
+    // trim_data layout: children are NODE indices at [1], [2]; node k starts at the k-th
+    // record boundary, so build the offset table first (inner nodes have 3 elements,
+    // leaves n+6).
+    if (layout == AI_TREE_LAYOUT_TRIM)
+        return fail(AI_ERR_UNSUPPORTED, "trim_data tree layout: the reference's own evaluator indexes it "
+                    "inconsistently (approximator.py:202-206 vs :275-290); flatten on the host instead");
+    const int stride = n + 6;
+    if (n_elems % stride) return fail(AI_ERR_TABLE, "tree_1d length %lld is not a multiple of the node stride %d",
+                                      (long long)n_elems, stride);
+    const int64_t n_nodes = n_elems / stride;
+    struct Frame { int64_t off; int state; };
+    std::vector<Frame> stack;
+    stack.push_back({0, 0});
+    int64_t visited = 0;
+    while (!stack.empty()) {
+        Frame& fr = stack.back();
+        const int64_t o = fr.off;
+        if (o < 0 || o + stride > n_elems || (o % stride)) return fail(AI_ERR_TABLE, "child offset %lld out of range", (long long)o);
+        const int64_t lo = (int64_t)at(o + n + 4), ro = (int64_t)at(o + n + 5);
+        const bool leaf = (lo == o) || (ro == o);
+        if (leaf) {
+            a.push_back(at(o + n + 2));
+            b.push_back(at(o + n + 3));
+            for (int j = 0; j <= n; ++j) coef.push_back(at(o + 1 + j));
+            stack.pop_back();
+        } else if (fr.state == 0) {
+            fr.state = 1;
+            stack.push_back({lo, 0});
+        } else if (fr.state == 1) {
+            fr.state = 2;
+            stack.push_back({ro, 0});
+        } else {
+            stack.pop_back();
+        }
+        if (++visited > 4 * n_nodes + 8) return fail(AI_ERR_TABLE, "tree_1d child links form a cycle");
+        if ((int64_t)stack.size() > n_nodes + 1) return fail(AI_ERR_TABLE, "tree_1d deeper than its node count");
+    }
+    const int64_t L = (int64_t)a.size();
+    if (L < 1) return fail(AI_ERR_TABLE, "tree has no leaves");
+    for (int64_t k = 0; k + 1 < L; ++k)
+        if (b[k] != a[k + 1]) return fail(AI_ERR_TABLE, "leaves %lld and %lld are not contiguous (%.17g != %.17g)",
+                                          (long long)k, (long long)k + 1, b[k], a[k + 1]);
+    (void)num_levels;
+    ai_table* t = new ai_table;
+    t->basis = basis; t->order = order; t->dtype = dtype; t->device = device; t->L = L;
+    t->breaks = a;
+    t->breaks.push_back(b.back());
+    t->coef = coef;
+    rc = finish_table(t);
+    if (rc) { ai_table_destroy(t); return rc; }
+    *out = t;
+    return AI_OK;
+}
+
+int ai_table_destroy(ai_table_t* t) {
+    if (!t) return AI_OK;
+    DeviceGuard guard(t->device);
+    pipe_destroy(t);
+    if (t->d_image) cudaFree(t->d_image);
+    delete t;
+    return AI_OK;
+}
+
+int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
+    if (!t || !info) return fail(AI_ERR_INVALID, "table or info is NULL");
+    info->basis = t->basis; info->order = t->order; info->dtype = t->dtype; info->device = t->device;
+    info->n_leaves = t->L;
+    info->grid_cells = t->G; info->grid_log2_scale = t->p; info->search_steps = t->K;
+    info->record_stride = t->rstride;
+    info->image_bytes = t->view.image_bytes;
+    info->smem_resident = t->smem_resident;
+    info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;
+    info->lower_bound = t->breaks.front(); info->upper_bound = t->breaks.back();
+    return AI_OK;
+}
+
+int ai_table_get_flat(const ai_table_t* t, void* breaks, void* coef) {
+    if (!t) return fail(AI_ERR_INVALID, "table is NULL");
+    if (t->dtype == AI_DTYPE_F32) {
+        if (breaks) for (size_t k = 0; k < t->breaks.size(); ++k) static_cast<float*>(breaks)[k] = (float)t->breaks[k];
+        if (coef) for (size_t k = 0; k < t->coef.size(); ++k) static_cast<float*>(coef)[k] = (float)t->coef[k];
+    } else {
+        if (breaks) std::memcpy(breaks, t->breaks.data(), t->breaks.size() * sizeof(double));
+        if (coef) std::memcpy(coef, t->coef.data(), t->coef.size() * sizeof(double));
+    }
+    return AI_OK;
+}
+
+int ai_eval_f32(const ai_table_t* t, const float* x, float* y, int64_t n, void* s) { return eval_entry<float>(t, x, y, n, s); }
+int ai_eval_f64(const ai_table_t* t, const double* x, double* y, int64_t n, void* s) { return eval_entry<double>(t, x, y, n, s); }
+int ai_eval_index_f32(const ai_table_t* t, const float* x, int32_t* i, int64_t n, void* s) { return index_entry<float>(t, x, i, n, s); }
+int ai_eval_index_f64(const ai_table_t* t, const double* x, int32_t* i, int64_t n, void* s) { return index_entry<double>(t, x, i, n, s); }
+int ai_eval_sum_f32(const ai_table_t* t, const float* x, double* r, int64_t n, void* s) { return sum_entry<float>(t, x, r, n, s); }
+int ai_eval_sum_f64(const ai_table_t* t, const double* x, double* r, int64_t n, void* s) { return sum_entry<double>(t, x, r, n, s); }
+int ai_eval_host_f32(const ai_table_t* t, const float* x, float* y, int64_t n, double* ms) { return host_entry<float>(t, x, y, n, ms); }
+int ai_eval_host_f64(const ai_table_t* t, const double* x, double* y, int64_t n, double* ms) { return host_entry<double>(t, x, y, n, ms); }
+
+int ai_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return fail(AI_ERR_INVALID, "bad arguments");
+    AI_CUDA(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault));
+    return AI_OK;
+}
+
+int ai_host_free(void* p) {
+    if (p) AI_CUDA(cudaFreeHost(p));
+    return AI_OK;
+}
+
+int ai_measure_fma_peak(int device, int dtype, double* tflops) {
+    if (!tflops) return fail(AI_ERR_INVALID, "tflops is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", device);
+    cudaDeviceProp prop;
+    AI_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    void* out = nullptr;
+    AI_CUDA(cudaMalloc(&out, 64));
+    cudaEvent_t e0, e1;
+    AI_CUDA(cudaEventCreate(&e0));
+    AI_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        AI_CUDA(cudaEventRecord(e0, 0));
+        if (dtype == AI_DTYPE_F32) fma_chain_kernel<float><<<grid, 256>>>(static_cast<float*>(out), iters, 1.0000001f, 1e-9f);
+        else fma_chain_kernel<double><<<grid, 256>>>(static_cast<double*>(out), iters, 1.0000000001, 1e-12);
+        AI_CUDA(cudaEventRecord(e1, 0));
+        AI_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        AI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    AI_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+    *tflops = flops / ((double)best * 1e-3) / 1e12;
+    return AI_OK;
+}
+
+int ai_copy_f32(const float* x, float* y, int64_t n, int device, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !y))) return fail(AI_ERR_INVALID, "bad arguments");
+    if ((reinterpret_cast<uintptr_t>(x) % 16) || (reinterpret_cast<uintptr_t>(y) % 16) || (n % 4))
+        return fail(AI_ERR_INVALID, "ai_copy_f32 needs 16-byte aligned buffers and n %% 4 == 0");
+    if (n == 0) return AI_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", device);
+    cudaDeviceProp prop;
+    AI_CUDA(cudaGetDeviceProperties(&prop, device));
+    copy_kernel<float4><<<prop.multiProcessorCount * 8, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n / 4);
+    AI_CUDA(cudaGetLastError());
+    return AI_OK;
+}
+
+}  // extern "C"

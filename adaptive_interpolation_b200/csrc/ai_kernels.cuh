@@ -1,0 +1,333 @@
+// ai_kernels.cuh -- device side of the B200 evaluator (sm_100a).
+//
+// One kernel template eval_kernel<BASIS, ORDER, T> replaces every kernel text the reference
+// generates per approximation (adaptive_interpolation/generate.py: gen_cheb :62-102, gen_leg
+// :106-144, gen_mono :28-57, gen_ispc :191-400).  Per point it does what that text does --
+// find the leaf interval, rescale to [-1,1], evaluate the order-n polynomial -- but
+//   * the interval is found with an EXACT power-of-two grid (cell = floor(x * 2^p), no rounding
+//     anywhere) plus, only for tables whose breakpoints do not sit on cell edges, a fixed-trip
+//     branch-free binary search over the stored breakpoints.  The result equals the reference's
+//     BST walk (approximator.py:285-290) for every input, which the reference's own O(1) map
+//     `f[(int)(S*x - O)]` (generate.py:301) does not;
+//   * the table (grid, breakpoints, per-leaf records) is staged once per CTA into shared memory;
+//   * x / y stream through HBM as 16-byte vectors with streaming cache hints.
+// The work is HBM-bound integer/FP32/FP64 streaming: no tensor cores, by design.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ai {
+
+constexpr int kBlock = 256;        // threads per CTA
+constexpr int kUnroll = 4;         // 16-byte vectors in flight per thread per tile
+
+enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
+
+// Everything a kernel needs to know about a table; passed by value (kernel parameter space).
+struct TableView {
+    const unsigned char* image;    // packed image in global memory (16-byte aligned)
+    int image_bytes;               // multiple of 16
+    int off_first;                 // uint16 first[G]       : leaf holding the left edge of cell g
+    int off_breaks;                // T breaks[L+1+pad]     : sorted breakpoints, +inf padded
+    int off_records;               // T rec[L][R]           : [a, 2/(b-a), c0..cn, pad]
+    int n_leaves;                  // L
+    int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
+    int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
+    double scale;                  // 2^p (exact in T)
+    double lo, hi;                 // g0 and g0+G-1 as floating point (exact in T)
+    double inv_order;              // T(1./n) widened: the Legendre-like recurrence's divisor
+};
+
+// ---------------------------------------------------------------------------------- helpers
+template <typename T> struct Vec;
+template <> struct Vec<float>  { using type = float4;  static constexpr int N = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename T> __host__ __device__ constexpr int rec_header(int basis) { return basis == kMono ? 0 : 2; }
+// record stride in elements: odd, so that lanes on different leaves hit different banks
+__host__ __device__ constexpr int rec_stride(int basis, int order) {
+    return ((order + 1 + (basis == kMono ? 0 : 2)) | 1);
+}
+
+__device__ __forceinline__ float  fma_(float a, float b, float c)    { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// cell index relative to the first cell, clamped to the grid.  x*scale is exact (power of two),
+// floor is exact, so cell(x) is the true floor(x*2^p) for every finite x.  NaN lands on a valid
+// cell (F2I(NaN) = 0 before the integer clamp / fminf(NaN, hi) = hi).
+__device__ __forceinline__ int cell_of(float x, float scale, float lo, float hi, int g0) {
+    float u = x * scale;
+    u = fmaxf(fminf(u, hi), lo);
+    return __float2int_rd(u) - g0;
+}
+__device__ __forceinline__ int cell_of(double x, double scale, int glo, int ghi) {
+    // cvt.rmi.s32.f64 saturates; clamp in the integer domain BEFORE subtracting g0 (no overflow)
+    const int gi = __double2int_rd(x * scale);
+    return min(max(gi, glo), ghi) - glo;
+}
+
+template <typename T> struct Lookup {
+    T scale, lo, hi;
+    int g0, ghi, kstep, lmax;
+    const uint16_t* first;
+    const T* breaks;
+
+    __device__ __forceinline__ void init(const TableView& tv, const unsigned char* smem) {
+        scale = (T)tv.scale; lo = (T)tv.lo; hi = (T)tv.hi;
+        g0 = tv.g0; ghi = (int)tv.hi; kstep = tv.kstep; lmax = tv.n_leaves - 1;
+        first = reinterpret_cast<const uint16_t*>(smem + tv.off_first);
+        breaks = reinterpret_cast<const T*>(smem + tv.off_breaks);
+    }
+    // grid guess: the leaf holding the left edge of x's cell.  Exact answer when kstep == 0.
+    __device__ __forceinline__ int guess(T x) const {
+        int g;
+        if constexpr (sizeof(T) == 4) {
+            g = cell_of(x, scale, lo, hi, g0);
+        } else {
+            g = cell_of(x, scale, g0, ghi);
+        }
+        return first[g];
+    }
+    // one step of the branch-free forward binary search (step s = 2^k); breaks[] is +inf padded
+    __device__ __forceinline__ int refine(T x, int i, int s) const {
+        const int j = i + s;
+        return !(x < breaks[j]) ? j : i;
+    }
+    __device__ __forceinline__ int finish(int i) const { return min(i, lmax); }
+
+    // leaf ordinals of N points held in registers.  The search loop runs over steps on the
+    // outside and points on the inside, so the N dependent chains interleave (ILP) and the
+    // only branch is the warp-uniform trip count.
+    template <int N>
+    __device__ __forceinline__ void leaves(const T (&x)[N], int (&i)[N]) const {
+#pragma unroll
+        for (int e = 0; e < N; ++e) i[e] = guess(x[e]);
+        if (kstep) {                      // tables whose breakpoints are off the grid
+            for (int s = kstep; s; s >>= 1) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) i[e] = refine(x[e], i[e], s);
+            }
+#pragma unroll
+            for (int e = 0; e < N; ++e) i[e] = finish(i[e]);
+        }
+    }
+    __device__ __forceinline__ int leaf(T x) const {
+        T xs[1] = {x};
+        int is[1];
+        leaves<1>(xs, is);
+        return is[0];
+    }
+    // as leaf(), but also reproduces the reference for NaN: every `mid > x` test is false, the
+    // walk always goes right and ends on the last leaf (approximator.py:287-290).
+    __device__ __forceinline__ int leaf_nan_exact(T x) const {
+        int i = leaf(x);
+        return (x != x) ? lmax : i;
+    }
+};
+
+// ------------------------------------------------------------------------- basis evaluation
+// rec points at the leaf record in shared memory.  Arithmetic follows the reference's operation
+// order (adapt.py:97-139 as called from approximator.py:291-295) with each multiply-add pair
+// fused; see DESIGN.md "numerics" for the measured deviation from the reference evaluator.
+template <int BASIS, int ORDER, typename T>
+__device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order) {
+    if constexpr (BASIS == kMono) {
+        // adapt.py:139 sum c_i x^i on the RAW x; Horner as generate.py:48-52
+        T acc = rec[ORDER];
+#pragma unroll
+        for (int j = ORDER - 1; j >= 0; --j) acc = fma_(acc, x, rec[j]);
+        return acc;
+    } else {
+        const T a = rec[0], s = rec[1];
+        const T* c = rec + 2;
+        // adapt.py:130  xscaled = 2*(x-a)/(b-a) - 1, with 2/(b-a) precomputed per leaf in T
+        const T t = fma_(x - a, s, (T)-1);
+        if constexpr (ORDER == 0) {
+            return c[0];
+        } else if constexpr (BASIS == kCheb) {
+            // adapt.py:111-120  T0=1, T1=t, Ti = (2t) T(i-1) - T(i-2);  y = sum c_i T_i
+            const T t2 = t + t;
+            T acc = fma_(c[1], t, c[0]);
+            T p0 = (T)1, p1 = t;
+#pragma unroll
+            for (int j = 2; j <= ORDER; ++j) {
+                const T pn = fma_(t2, p1, -p0);
+                acc = fma_(c[j], pn, acc);
+                p0 = p1; p1 = pn;
+            }
+            return acc;
+        } else {
+            // adapt.py:97-108  L0=1, L1=t, Li = ((2i-1) t L(i-1) + (i-1) L(i-2)) * (1./n)
+            // -- note the PLUS sign and the constant divisor n: this is the reference's basis,
+            // not the Legendre polynomials; the saved coefficients were fitted in it.
+            T acc = fma_(c[1], t, c[0]);
+            T p0 = (T)1, p1 = t;
+#pragma unroll
+            for (int j = 2; j <= ORDER; ++j) {
+                const T first = ((T)(2 * j - 1) * t);
+                const T pn = fma_(first, p1, (T)(j - 1) * p0) * inv_order;
+                acc = fma_(c[j], pn, acc);
+                p0 = p1; p1 = pn;
+            }
+            return acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------- streaming access
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
+
+// stage the packed table image into shared memory (16-byte chunks, whole CTA)
+__device__ __forceinline__ void stage_image(const TableView& tv, unsigned char* smem) {
+    const int4* src = reinterpret_cast<const int4*>(tv.image);
+    int4* dst = reinterpret_cast<int4*>(smem);
+    for (int k = threadIdx.x; k < tv.image_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------- the hot kernel
+// Work split (host computes it, see launch_eval): [0, head) scalar, then nvec 16-byte vectors,
+// then a scalar tail.  head/tail are < Vec::N elements unless x and y are misaligned relative
+// to each other, in which case head == n and everything takes the scalar loop.
+template <int BASIS, int ORDER, typename T>
+__global__ void __launch_bounds__(kBlock)
+eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
+            long long n, long long head, long long nvec) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_image(tv, smem);
+
+    Lookup<T> lk;
+    lk.init(tv, smem);
+    const T* records = reinterpret_cast<const T*>(smem + tv.off_records);
+    constexpr int R = rec_stride(BASIS, ORDER);
+    const T inv_order = (T)tv.inv_order;
+
+    auto f = [&](T xv) -> T {
+        const int i = lk.leaf(xv);
+        return eval_leaf<BASIS, ORDER, T>(records + i * R, xv, inv_order);
+    };
+
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    const V* __restrict__ xv = reinterpret_cast<const V*>(x + head);
+    V* __restrict__ yv = reinterpret_cast<V*>(y + head);
+
+    constexpr long long kTile = (long long)kBlock * kUnroll;       // vectors per tile
+    constexpr int NE = kUnroll * VN;                               // points per thread per tile
+    const long long full_tiles = nvec / kTile;
+    for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
+        const long long base = tile * kTile + threadIdx.x;
+        V in[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) in[u] = ld_stream(xv + base + (long long)u * kBlock);
+        T xs[NE];
+        int li[NE];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if constexpr (VN == 4) {
+                xs[4 * u] = in[u].x; xs[4 * u + 1] = in[u].y; xs[4 * u + 2] = in[u].z; xs[4 * u + 3] = in[u].w;
+            } else {
+                xs[2 * u] = in[u].x; xs[2 * u + 1] = in[u].y;
+            }
+        }
+        lk.template leaves<NE>(xs, li);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T>(records + li[e] * R, xs[e], inv_order);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            V out;
+            if constexpr (VN == 4) {
+                out.x = xs[4 * u]; out.y = xs[4 * u + 1]; out.z = xs[4 * u + 2]; out.w = xs[4 * u + 3];
+            } else {
+                out.x = xs[2 * u]; out.y = xs[2 * u + 1];
+            }
+            st_stream(yv + base + (long long)u * kBlock, out);
+        }
+    }
+    // remainder vectors (less than one tile), spread over the whole grid
+    const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kBlock;
+    for (long long v = full_tiles * kTile + gtid; v < nvec; v += gstride) {
+        V in = ld_stream(xv + v), out;
+        if constexpr (VN == 4) {
+            out.x = f(in.x); out.y = f(in.y); out.z = f(in.z); out.w = f(in.w);
+        } else {
+            out.x = f(in.x); out.y = f(in.y);
+        }
+        st_stream(yv + v, out);
+    }
+    // scalar head and tail
+    for (long long k = gtid; k < head; k += gstride) y[k] = f(x[k]);
+    for (long long k = head + nvec * VN + gtid; k < n; k += gstride) y[k] = f(x[k]);
+}
+
+// The reference's no-"output" variant (generate.py:284,392-394): reduce y instead of storing it.
+template <int BASIS, int ORDER, typename T>
+__global__ void __launch_bounds__(kBlock)
+eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_image(tv, smem);
+    Lookup<T> lk;
+    lk.init(tv, smem);
+    const T* records = reinterpret_cast<const T*>(smem + tv.off_records);
+    constexpr int R = rec_stride(BASIS, ORDER);
+    const T inv_order = (T)tv.inv_order;
+    double acc = 0.0;
+    const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kBlock;
+    for (long long k = gtid; k < n; k += gstride) {
+        const T xv = __ldcs(x + k);
+        const int i = lk.leaf(xv);
+        acc += (double)eval_leaf<BASIS, ORDER, T>(records + i * R, xv, inv_order);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double wsum[kBlock / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) s += wsum[w];
+        atomicAdd(result, s);
+    }
+}
+
+// leaf ordinal only: the bit-exactness check and the lookup-only ablation
+// (the reference's "test first loop", generate.py:320-332)
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+index_kernel(const TableView tv, const T* __restrict__ x, int32_t* __restrict__ idx, long long n) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_image(tv, smem);
+    Lookup<T> lk;
+    lk.init(tv, smem);
+    const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kBlock;
+    for (long long k = gtid; k < n; k += gstride) idx[k] = lk.leaf_nan_exact(__ldcs(x + k));
+}
+
+// ------------------------------------------------------------------------- launch plumbing
+struct LaunchCfg {
+    int grid;
+    int smem_bytes;
+    cudaStream_t stream;
+};
+
+// One translation unit per (basis, dtype) -- see ai_inst.cuh -- each exporting:
+#define AI_DECLARE_UNIT(NAME, T)                                                                   \
+    cudaError_t launch_eval_##NAME(int order, const LaunchCfg&, const TableView&, const T*, T*,    \
+                                   long long, long long, long long);                               \
+    cudaError_t launch_sum_##NAME(int order, const LaunchCfg&, const TableView&, const T*, double*, \
+                                  long long);                                                      \
+    cudaError_t prepare_##NAME(int order, int smem_bytes, int* blocks_per_sm);
+AI_DECLARE_UNIT(cheb_f32, float)
+AI_DECLARE_UNIT(cheb_f64, double)
+AI_DECLARE_UNIT(leg_f32, float)
+AI_DECLARE_UNIT(leg_f64, double)
+AI_DECLARE_UNIT(mono_f32, float)
+AI_DECLARE_UNIT(mono_f64, double)
+#undef AI_DECLARE_UNIT
+
+}  // namespace ai

@@ -1,0 +1,235 @@
+"""Host-side table handling: flatten the reference's Approximator data into the SoA form the
+CUDA library consumes, and own the device tables.
+
+Reference data this reads (never writes):
+  adaptive_interpolation/approximator.py:118-136   tree_1d(): AoS node array, stride order+6,
+        node = [mid, c0..cn, a, b, left_off, right_off], child links are ELEMENT offsets stored
+        as table-dtype floats, leaves link to themselves (:196-199)
+  adaptive_interpolation/approximator.py:211-216   interval_a / interval_b / coeff SoA lists
+  run_test.py:242-246                              tables are cast to the table dtype before use
+
+`flatten(approx)` works on any object carrying those attributes: the reference's own
+Approximator (all three pickle schema versions), this package's stand-in
+(approximator.py here), or a golden fixture record.
+"""
+import ctypes
+import json
+import os
+import weakref
+
+import numpy as np
+
+from . import _cabi
+
+_GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                           "tests", "golden", "tables")
+
+
+class FlatTable(object):
+    """Sorted breakpoints + per-leaf coefficients, in the table dtype."""
+
+    def __init__(self, basis, order, dtype, breaks, coef):
+        self.basis = str(basis)
+        self.order = int(order)
+        self.dtype = np.dtype(dtype)
+        self.breaks = np.ascontiguousarray(breaks, dtype=self.dtype)
+        self.coef = np.ascontiguousarray(coef, dtype=self.dtype).reshape(len(self.breaks) - 1, self.order + 1)
+        if self.basis not in _cabi.BASIS_IDS:
+            raise Exception("Incorrect basis provided: monomial, chebyshev, legendre.")
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise Exception("Incorrect data type specified")
+
+    @property
+    def n_leaves(self):
+        return len(self.breaks) - 1
+
+    @property
+    def lower_bound(self):
+        return self.breaks[0]
+
+    @property
+    def upper_bound(self):
+        return self.breaks[-1]
+
+
+def flatten_tree_1d(tree_1d, order):
+    """Enumerate the leaves of a standard-layout tree_1d left to right.
+
+    Follows the child links exactly as Approximator.evaluate does (approximator.py:285-290):
+    offsets [n+4] / [n+5] cast with int().  Returns (a, b, coef[L, n+1]) in tree_1d's dtype."""
+    t = np.asarray(tree_1d)
+    n = int(order)
+    stride = n + 6
+    if t.ndim != 1 or len(t) == 0 or len(t) % stride:
+        raise ValueError("tree_1d of length %d is not a whole number of stride-%d nodes" % (len(t), stride))
+    a, b, coef = [], [], []
+    stack = [0]
+    seen = 0
+    while stack:
+        o = stack.pop()
+        seen += 1
+        if seen > len(t):
+            raise ValueError("tree_1d child links form a cycle")
+        if o < 0 or o + stride > len(t) or o % stride:
+            raise ValueError("tree_1d child offset %d out of range" % o)
+        lo, ro = int(t[o + n + 4]), int(t[o + n + 5])
+        if lo == o or ro == o:
+            a.append(t[o + n + 2])
+            b.append(t[o + n + 3])
+            coef.append(t[o + 1:o + n + 2])
+        else:
+            stack.append(ro)        # right first so that left pops first: left-to-right order
+            stack.append(lo)
+    a = np.array(a, dtype=t.dtype)
+    b = np.array(b, dtype=t.dtype)
+    if np.any(a[1:] != b[:-1]):
+        k = int(np.nonzero(a[1:] != b[:-1])[0][0])
+        raise ValueError("leaves %d and %d are not contiguous (%r != %r)" % (k, k + 1, b[k], a[k + 1]))
+    return a, b, np.array(coef, dtype=t.dtype).reshape(len(a), n + 1)
+
+
+def table_dtype(approx):
+    dt = getattr(approx, "dtype", None)
+    if dt is None:
+        dt = np.asarray(approx.tree_1d).dtype
+    return np.dtype(dt)
+
+
+def flatten(approx):
+    """Approximator-like object -> FlatTable, cross-checked against its SoA arrays when present."""
+    if isinstance(approx, FlatTable):
+        return approx
+    opts = list(getattr(approx, "optimizations", []) or [])
+    if "trim_data" in opts:
+        raise Exception("trim_data tables are not supported: the reference's own evaluator indexes "
+                        "that layout inconsistently (approximator.py:202-206 vs 275-290)")
+    dt = table_dtype(approx)
+    n = int(approx.max_order)
+    tree_1d = np.asarray(approx.tree_1d, dtype=dt)          # run_test.py:242 cast
+    a, b, coef = flatten_tree_1d(tree_1d, n)
+    ia = getattr(approx, "interval_a", None)
+    if ia is not None and len(ia) == len(a):
+        ib, co = approx.interval_b, approx.coeff
+        ok = (np.array_equal(np.asarray(ia, dtype=dt), a) and np.array_equal(np.asarray(ib, dtype=dt), b)
+              and np.array_equal(np.asarray(co, dtype=dt).reshape(len(a), n + 1), coef))
+        if not ok:
+            raise ValueError("Approximator tree_1d and interval_a/interval_b/coeff disagree")
+    breaks = np.concatenate([a, b[-1:]])
+    return FlatTable(approx.basis, n, dt, breaks, coef)
+
+
+class GoldenRecord(object):
+    """A frozen reference table + the reference's own evaluation of it (tests/golden/make_golden.py).
+    Carries the attributes of the reference Approximator that the hot path reads."""
+
+    def __init__(self, path):
+        d = np.load(path, allow_pickle=False)
+        self.meta = json.loads(str(d["meta"]))
+        m = self.meta
+        self.name = m["name"]
+        self.basis = m["basis"]
+        self.max_order = m["order"]
+        self.num_levels = m["num_levels"]
+        self.dtype = np.dtype(m["dtype"]).type
+        self.dtype_name = m["dtype_name"]
+        self.lower_bound = self.dtype(m["lower_bound"])
+        self.upper_bound = self.dtype(m["upper_bound"])
+        self.optimizations = list(m["optimizations"])
+        self.allowed_error = m["allowed_error"]
+        self.fmax = m["fmax"]
+        self.tree_1d = d["tree_1d"]
+        self.interval_a = list(d["interval_a"])
+        self.interval_b = list(d["interval_b"])
+        self.coeff = list(d["coeff"])
+        self.map = d["map"]
+        self.cmap = d["cmap"]
+        self.code, self.size, self.vector_width = 0, None, None
+        self.kernal = self.queue = self.tree_dev = self.x_dev = self.y_dev = None
+        self.x, self.y_ref, self.idx_ref, self.f_true = d["x"], d["y_ref"], d["idx_ref"], d["f_true"]
+
+
+def golden_names():
+    if not os.path.isdir(_GOLDEN_DIR):
+        return []
+    return sorted(f[:-4] for f in os.listdir(_GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    return GoldenRecord(os.path.join(_GOLDEN_DIR, name + ".npz"))
+
+
+# ------------------------------------------------------------------------- device tables
+class DeviceTable(object):
+    """Owns one ai_table_t handle (a table resident on one GPU)."""
+
+    def __init__(self, flat, device=0):
+        self.flat = flat
+        self.device = int(device)
+        L = _cabi.lib()
+        h = ctypes.c_void_p()
+        _cabi.check(L.ai_table_create(
+            _cabi.BASIS_IDS[flat.basis], flat.order,
+            _cabi.DTYPE_F32 if flat.dtype == np.float32 else _cabi.DTYPE_F64,
+            flat.n_leaves, flat.breaks.ctypes.data, flat.coef.ctypes.data, self.device, ctypes.byref(h)))
+        self._h = h
+        self._finalizer = weakref.finalize(self, L.ai_table_destroy, h)
+
+    @classmethod
+    def from_tree_1d(cls, basis, order, dtype, num_levels, tree_1d, device=0):
+        """Flattening done inside the library (ai_table_create_from_tree)."""
+        self = cls.__new__(cls)
+        L = _cabi.lib()
+        dt = np.dtype(dtype)
+        t = np.ascontiguousarray(tree_1d, dtype=dt)
+        h = ctypes.c_void_p()
+        _cabi.check(L.ai_table_create_from_tree(
+            _cabi.BASIS_IDS[basis], int(order), _cabi.DTYPE_F32 if dt == np.float32 else _cabi.DTYPE_F64,
+            int(num_levels), 0, t.ctypes.data, len(t), int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._finalizer = weakref.finalize(self, L.ai_table_destroy, h)
+        info = self.info()
+        nl = info["n_leaves"]
+        breaks = np.empty(nl + 1, dtype=dt)
+        coef = np.empty(nl * (int(order) + 1), dtype=dt)
+        _cabi.check(L.ai_table_get_flat(h, breaks.ctypes.data, coef.ctypes.data))
+        self.flat = FlatTable(basis, order, dt, breaks, coef)
+        return self
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        info = _cabi.TableInfo()
+        _cabi.check(_cabi.lib().ai_table_get_info(self._h, ctypes.byref(info)))
+        return info.as_dict()
+
+    def close(self):
+        self._finalizer()
+
+    # raw-pointer entry points (device pointers as ints, stream as int/None)
+    def eval_ptr(self, x_ptr, y_ptr, n, stream=None):
+        fn = _cabi.lib().ai_eval_f32 if self.flat.dtype == np.float32 else _cabi.lib().ai_eval_f64
+        _cabi.check(fn(self._h, x_ptr, y_ptr, int(n), stream))
+
+    def index_ptr(self, x_ptr, idx_ptr, n, stream=None):
+        fn = _cabi.lib().ai_eval_index_f32 if self.flat.dtype == np.float32 else _cabi.lib().ai_eval_index_f64
+        _cabi.check(fn(self._h, x_ptr, idx_ptr, int(n), stream))
+
+    def sum_ptr(self, x_ptr, result_ptr, n, stream=None):
+        fn = _cabi.lib().ai_eval_sum_f32 if self.flat.dtype == np.float32 else _cabi.lib().ai_eval_sum_f64
+        _cabi.check(fn(self._h, x_ptr, result_ptr, int(n), stream))
+
+    def eval_host(self, x, y=None):
+        """The reference-facing call on HOST arrays: H2D + kernel + D2H pipelined inside the
+        library (ai_eval_host_*).  Returns (y, kernel_ms)."""
+        x = np.ascontiguousarray(x, dtype=self.flat.dtype)
+        if y is None:
+            y = np.empty_like(x)
+        if y.dtype != self.flat.dtype or not y.flags.c_contiguous or y.size != x.size:
+            raise ValueError("y must be a contiguous %s array of x's size" % self.flat.dtype)
+        ms = ctypes.c_double(0.0)
+        fn = _cabi.lib().ai_eval_host_f32 if self.flat.dtype == np.float32 else _cabi.lib().ai_eval_host_f64
+        _cabi.check(fn(self._h, x.ctypes.data, y.ctypes.data, x.size, ctypes.byref(ms)))
+        return y, ms.value

@@ -1,0 +1,373 @@
+"""Parity of the CUDA path with the reference evaluator, through the C ABI.  Needs a B200.
+
+Bar (BASELINE.json north_star): leaf indices bit-exact with the reference's BST walk; values
+within a few ulp of the reference CPU evaluation and inside the interpolant's error bound.
+
+"ulp" here is eps * sum_i |c_i B_i(x)| -- the magnitude every evaluation order's rounding errors
+live on (for a Chebyshev series it is ~ max|f|; J0 has zeros, so ulps of y itself would be
+meaningless there -- SURVEY.md section 7 "value tolerance").
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import oracle_np
+import adaptive_interpolation_b200.adaptive_interpolation as adapt_i
+import adaptive_interpolation_b200.generate as generate
+from adaptive_interpolation_b200 import _cabi, approximator as app, tables
+from conftest import ROOT, all_golden_names, golden, value_tolerance
+
+pytestmark = pytest.mark.gpu
+
+NAMES = all_golden_names()
+SAVED = [n for n in NAMES if n.startswith("approx")]
+# GPU (fused multiply-add, precomputed 2/(b-a)) vs the reference's Python evaluator.
+# The reference's own generated kernel differs from its Python evaluator by up to 8.3 of these
+# units (tests/test_oracle.py::test_reference_generated_kernel); we hold the GPU to 12.
+GPU_ULPS = 12
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def dev_table(name, device=0):
+    return tables.DeviceTable(tables.flatten(golden(name)), device)
+
+
+def to_dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_eval(tab, x):
+    xd = to_dev(np.asarray(x, dtype=tab.flat.dtype))
+    yd = torch.empty_like(xd)
+    tab.eval_ptr(xd.data_ptr(), yd.data_ptr(), xd.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return yd.cpu().numpy()
+
+
+def gpu_index(tab, x):
+    xd = to_dev(np.asarray(x, dtype=tab.flat.dtype))
+    idx = torch.empty(xd.numel(), dtype=torch.int32, device="cuda")
+    tab.index_ptr(xd.data_ptr(), idx.data_ptr(), xd.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return idx.cpu().numpy()
+
+
+def report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as fh:
+        fh.write(json.dumps(kw) + "\n")
+
+
+# ------------------------------------------------------------------ golden vectors, all tables
+@pytest.mark.parametrize("name", NAMES)
+def test_index_bit_exact_vs_reference(name):
+    g = golden(name)
+    tab = dev_table(name)
+    assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_values_vs_reference(name):
+    g = golden(name)
+    tab = dev_table(name)
+    y = gpu_eval(tab, g.x)
+    _, _, cond = oracle.c_eval_tree(g.tree_1d, g.max_order, g.num_levels, g.basis, g.x)
+    fin = np.isfinite(g.y_ref) & np.isfinite(cond)
+    assert np.all(~np.isfinite(y[~np.isfinite(g.y_ref)]))        # inf / nan inputs stay non-finite
+    err = np.abs(y[fin].astype(np.float64) - g.y_ref[fin].astype(np.float64))
+    units = err / (np.finfo(g.dtype).eps * np.maximum(cond[fin], np.finfo(g.dtype).tiny))
+    report(test="values_vs_reference", table=name, max_units=float(units.max()),
+           bit_identical=float(np.mean(y[fin] == g.y_ref[fin])))
+    assert np.all(err <= value_tolerance(g.dtype, cond[fin], GPU_ULPS)), float(units.max())
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if not n.startswith("gen__cfg4")])
+def test_inside_error_bound(name):
+    """|y_gpu - f| / max|f| <= the interpolant's stated bound (adapt.py:180-198), allowing what
+    the reference's own evaluation already uses of it."""
+    g = golden(name)
+    tab = dev_table(name)
+    y = gpu_eval(tab, g.x).astype(np.float64)
+    dom = (g.x >= g.lower_bound) & (g.x < g.upper_bound) & np.isfinite(g.f_true)
+    rel = np.max(np.abs(y[dom] - g.f_true[dom])) / g.fmax
+    rel_ref = np.max(np.abs(g.y_ref[dom].astype(np.float64) - g.f_true[dom])) / g.fmax
+    report(test="error_bound", table=name, rel=rel, rel_ref=rel_ref, allowed=g.allowed_error)
+    assert rel <= max(rel_ref, g.allowed_error) + 16 * np.finfo(g.dtype).eps
+
+
+# ------------------------------------------------------------------ adversarial lookups
+@pytest.mark.parametrize("name", NAMES)
+def test_index_adversarial_neighbourhoods(name):
+    """Every breakpoint and its 4 nearest representable neighbours on both sides, cell edges of
+    the power-of-two grid, out-of-domain, +-inf, NaN, +-0, denormals."""
+    g = golden(name)
+    f = tables.flatten(g)
+    tab = dev_table(name)
+    info = tab.info()
+    dt = g.dtype
+    pts = [f.breaks]
+    lo, hi = f.breaks.copy(), f.breaks.copy()
+    for _ in range(4):
+        lo, hi = np.nextafter(lo, dt(-np.inf)), np.nextafter(hi, dt(np.inf))
+        pts += [lo.copy(), hi.copy()]
+    p = info["grid_log2_scale"]
+    edges = (np.arange(info["grid_cells"] + 2, dtype=np.float64)
+             + np.floor(float(f.breaks[0]) * 2.0 ** p) - 1) * 2.0 ** (-p)
+    edges = edges.astype(dt)
+    pts += [edges, np.nextafter(edges, dt(-np.inf)), np.nextafter(edges, dt(np.inf))]
+    tiny = np.finfo(dt).tiny
+    pts.append(np.array([np.inf, -np.inf, np.nan, 0.0, -0.0, tiny, -tiny, tiny / 4, -tiny / 4,
+                         np.finfo(dt).max, -np.finfo(dt).max, 1e30, -1e30], dtype=dt))
+    x = np.concatenate(pts).astype(dt)
+    assert np.array_equal(gpu_index(tab, x), oracle_np.leaf_index(f.breaks, x))
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("cells", [1, 7, 64])
+def test_index_exact_in_forced_search_mode(name, cells, monkeypatch):
+    """Cap the grid so that the bounded binary search does the work on every table."""
+    monkeypatch.setenv("AI_B200_MAX_CELLS", str(cells))
+    g = golden(name)
+    tab = dev_table(name)
+    info = tab.info()
+    assert info["grid_cells"] <= cells
+    if info["n_leaves"] > cells:
+        assert info["search_steps"] >= 1
+    assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
+    y = gpu_eval(tab, g.x)
+    monkeypatch.delenv("AI_B200_MAX_CELLS")
+    y0 = gpu_eval(dev_table(name), g.x)
+    assert np.array_equal(y, y0, equal_nan=True)                  # same leaf -> same arithmetic
+
+
+def test_saved_tables_need_no_search():
+    """All 27 saved approximations are dyadic: the exact grid alone resolves the leaf (K = 0)."""
+    for name in SAVED:
+        info = dev_table(name).info()
+        assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
+        assert info["image_bytes"] <= 48 * 1024
+    for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
+        assert dev_table(name).info()["search_steps"] >= 1
+
+
+# ------------------------------------------------------------------ larger seeded inputs vs oracle
+@pytest.mark.parametrize("name", ["approx__32o6-p1.19209289551e-06", "gen__cfg3_j0_cheb_o13_f64",
+                                  "gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64",
+                                  "approximations__64o5-p2.22044604925e-14", "gen__j0_mono_o13_f64",
+                                  "gen__cfg1_sinsin_cheb_o3_f64", "gen__sinsin_leg_o10_f64"])
+def test_million_points_vs_oracle(name):
+    g = golden(name)
+    f = tables.flatten(g)
+    tab = dev_table(name)
+    rng = np.random.default_rng(12345)
+    x = rng.uniform(float(f.breaks[0]), float(f.breaks[-1]), 1 << 20).astype(g.dtype)
+    x = np.minimum(x, np.nextafter(f.breaks[-1], g.dtype(-np.inf)))
+    y_o, idx_o, cond = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x, want_cond=True)
+    assert np.array_equal(gpu_index(tab, x), idx_o)
+    y = gpu_eval(tab, x)
+    err = np.abs(y.astype(np.float64) - y_o.astype(np.float64))
+    units = err / (np.finfo(g.dtype).eps * np.maximum(cond, np.finfo(g.dtype).tiny))
+    report(test="million_vs_oracle", table=name, max_units=float(units.max()))
+    assert np.all(err <= value_tolerance(g.dtype, cond, GPU_ULPS)), float(units.max())
+
+
+# ------------------------------------------------------------------ ragged sizes and alignment
+@pytest.mark.parametrize("name", ["approx__32o7-p1.19209289551e-06", "approx__64o7-p1.19209289551e-06"])
+def test_sizes_and_misalignment(name):
+    g = golden(name)
+    tab = dev_table(name)
+    rng = np.random.default_rng(5)
+    big = rng.uniform(0, 20, 70000).astype(g.dtype)
+    want = gpu_eval(tab, big)
+    xd = to_dev(big)
+    esz = big.itemsize
+    for n in (0, 1, 2, 3, 4, 5, 7, 31, 33, 1023, 4096, 4097, 16385, 65537):
+        for ox in (0, 1, 3):
+            for oy in (0, 1, 2):
+                buf = torch.full((n + 8,), float("nan"), dtype=xd.dtype, device="cuda")
+                tab.eval_ptr(xd.data_ptr() + ox * esz, buf.data_ptr() + oy * esz, n,
+                             torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                out = buf.cpu().numpy()
+                assert np.array_equal(out[oy:oy + n], want[ox:ox + n]), (n, ox, oy)
+                assert np.all(np.isnan(out[:oy])) and np.all(np.isnan(out[oy + n:]))   # no stray writes
+
+
+def test_create_from_tree_equals_create():
+    for name in ("approx__32o3-p1.19209289551e-06", "gen__cfg4_f1_leg_o7_f64", "gen__j0_mono_o5_f64"):
+        g = golden(name)
+        t1 = dev_table(name)
+        t2 = tables.DeviceTable.from_tree_1d(g.basis, g.max_order, g.dtype, g.num_levels, g.tree_1d)
+        assert np.array_equal(t1.flat.breaks, t2.flat.breaks) and np.array_equal(t1.flat.coef, t2.flat.coef)
+        assert np.array_equal(gpu_eval(t1, g.x), gpu_eval(t2, g.x), equal_nan=True)
+        i1, i2 = t1.info(), t2.info()
+        assert (i1["grid_cells"], i1["search_steps"]) == (i2["grid_cells"], i2["search_steps"])
+
+
+# ------------------------------------------------------------------ host-buffer entry point
+@pytest.mark.parametrize("name,n", [("approx__32o6-p1.19209289551e-06", (1 << 25) + 12345),
+                                    ("approx__64o7-p2.22044604925e-14", (1 << 23) + 77),
+                                    ("approx__32o6-p1.19209289551e-06", 1000)])
+def test_eval_host_pipeline(name, n):
+    """ai_eval_host_*: chunked H2D / kernel / D2H; more chunks than pipeline slots."""
+    g = golden(name)
+    tab = dev_table(name)
+    x = np.random.default_rng(3).uniform(0, 20, n).astype(g.dtype)
+    y, ms = tab.eval_host(x)
+    assert ms > 0
+    assert np.array_equal(y, gpu_eval(tab, x))
+    # pinned buffers from the library give the same result
+    p = ctypes.c_void_p()
+    _cabi.check(_cabi.lib().ai_host_alloc(ctypes.byref(p), 2 * x.nbytes))
+    try:
+        buf = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_byte)), (2 * x.nbytes,)).view(g.dtype)
+        buf[:n] = x
+        y2, _ = tab.eval_host(buf[:n], buf[n:])
+        assert np.array_equal(y2, y)
+    finally:
+        _cabi.check(_cabi.lib().ai_host_free(p))
+
+
+def test_eval_sum_variant():
+    """The reference's no-"output" kernel variant (generate.py:392-394): y reduced, not stored."""
+    for name in ("approx__32o6-p1.19209289551e-06", "gen__cfg3_j0_cheb_o13_f64"):
+        g = golden(name)
+        tab = dev_table(name)
+        x = np.random.default_rng(9).uniform(0, 20, 1 << 20).astype(g.dtype)
+        y = gpu_eval(tab, x).astype(np.float64)
+        xd = to_dev(x)
+        res = torch.zeros(1, dtype=torch.float64, device="cuda")
+        tab.sum_ptr(xd.data_ptr(), res.data_ptr(), xd.numel(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert abs(res.item() - y.sum()) <= 1e-9 * np.abs(y).sum()
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_error_codes():
+    L = _cabi.lib()
+    tab = dev_table("approx__32o6-p1.19209289551e-06")
+    x = torch.zeros(8, dtype=torch.float64, device="cuda")
+    assert L.ai_eval_f64(tab.handle, x.data_ptr(), x.data_ptr(), 8, None) == 5           # AI_ERR_DTYPE
+    assert L.ai_eval_f32(tab.handle, None, None, 8, None) == 1                           # NULL buffers
+    assert L.ai_eval_f32(tab.handle, x.data_ptr(), x.data_ptr(), -1, None) == 1
+    assert L.ai_eval_f32(tab.handle, None, None, 0, None) == 0                           # empty is fine
+    h = ctypes.c_void_p()
+    br = np.array([0.0, 2.0, 1.0, 3.0], dtype=np.float32)
+    co = np.zeros(3 * 4, dtype=np.float32)
+    assert L.ai_table_create(0, 3, 0, 3, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(h)) == 2   # unsorted
+    assert b"strictly increasing" in L.ai_last_error()
+    br[1] = np.nan
+    assert L.ai_table_create(0, 3, 0, 3, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(h)) == 2
+    assert L.ai_table_create(0, 3, 0, 0, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(h)) == 2   # no leaves
+    assert L.ai_table_create(0, 3, 0, 3, br.ctypes.data, co.ctypes.data, 99, ctypes.byref(h)) == 1  # bad device
+    g = golden("approx__32o6-p1.19209289551e-06")
+    bad = g.tree_1d[:-1].copy()
+    assert L.ai_table_create_from_tree(0, 6, 0, 5, 0, bad.ctypes.data, len(bad), 0, ctypes.byref(h)) == 2
+
+
+# ------------------------------------------------------------------ the Python surface
+def test_python_surface_matches_reference_calls():
+    """The calls of run_test.py:394-395, tests/generate_tests.py:23-27, demo.py:90-101."""
+    g = golden("approx__64o7-p1.19209289551e-06")
+    ap = app.Approximator.from_record(g)
+    x = g.x[np.isfinite(g.x)]
+    want = gpu_eval(dev_table(g.name), x)
+    adapt_i.generate_code(ap)
+    rt, out = adapt_i.run_approximation(x, ap)                    # vector_width = 1 -> timed path
+    assert isinstance(rt, float) and rt > 0 and np.array_equal(out, want)
+    ap.vector_width = None                                        # untimed one-shot path
+    rt, out = adapt_i.run_approximation(x, ap)
+    assert rt is None and np.array_equal(out, want)
+    assert np.array_equal(adapt_i.run_code(x, ap, True), want)
+    knl, queue, tree_dev = generate.build_code(ap)
+    assert "eval_kernel" in knl and ap.kernal == knl and isinstance(ap.queue, int)
+    sec, out = generate.run_single(x, ap)
+    assert sec > 0 and np.array_equal(out, want)
+    sec, out = generate.run_multi(x, ap)
+    assert sec > 0 and np.array_equal(out, want)
+    assert np.array_equal(np.array(ap.evaluate(x[:100])), want[:100])
+    # CUDA tensors in, CUDA tensor out, no copies
+    xd = to_dev(x)
+    sec, yd = generate.run_single(xd, ap)
+    assert yd.is_cuda and np.array_equal(yd.cpu().numpy(), want)
+    assert np.array_equal(generate.run_index(x, ap), oracle_np.leaf_index(tables.flatten(g).breaks, x))
+    # nothing un-picklable was left on the object
+    import pickle
+    pickle.dumps(ap)
+
+
+def test_reference_parity_test_intent():
+    """tests/generate_tests.py:27: ||app.evaluate(x) - run_code(x)||_inf / max|f| < 1e-12 (fp64)."""
+    for name in ("gen__cossin_cheb_o10_f64", "gen__sinsin_leg_o10_f64", "gen__cfg1_sinsin_cheb_o3_f64"):
+        g = golden(name)
+        ap = app.Approximator.from_record(g)
+        adapt_i.generate_code(ap)
+        dom = (g.x >= g.lower_bound) & (g.x <= g.upper_bound)
+        out = adapt_i.run_code(g.x[dom], ap, 1)
+        assert np.max(np.abs(out - g.y_ref[dom])) / g.fmax < 1e-12
+
+
+# ------------------------------------------------------------------ BASELINE sizes: properties
+def _device_uniform(n, lo, hi, dtype, seed):
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    x = torch.rand(n, dtype=dtype, device="cuda", generator=gen) * (hi - lo) + lo
+    return torch.clamp(x, max=float(np.nextafter(dtype_np(dtype)(hi), dtype_np(dtype)(-np.inf))))
+
+
+def dtype_np(t):
+    return np.float32 if t == torch.float32 else np.float64
+
+
+@pytest.mark.parametrize("name,log2n", [("approx__32o6-p1.19209289551e-06", 28),      # BASELINE config 2
+                                        ("gen__cfg3_j0_cheb_o13_f64", 30),            # BASELINE config 3
+                                        ("gen__cfg4_f1_leg_o7_f32", 28)])             # BASELINE config 4
+def test_full_size_properties(name, log2n):
+    g = golden(name)
+    f = tables.flatten(g)
+    tab = dev_table(name)
+    n = 1 << log2n
+    tdt = torch.float32 if g.dtype == np.float32 else torch.float64
+    x = _device_uniform(n, float(f.breaks[0]), float(f.breaks[-1]), tdt, seed=log2n)
+    y = torch.empty_like(x)
+    s = torch.cuda.current_stream().cuda_stream
+    tab.eval_ptr(x.data_ptr(), y.data_ptr(), n, s)
+    torch.cuda.synchronize()
+    # (a) a strided sample of the full run agrees with the oracle
+    step = n // (1 << 16)
+    xs, ys = x[::step].cpu().numpy(), y[::step].cpu().numpy()
+    y_o, idx_o, cond = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, xs, want_cond=True)
+    assert np.all(np.abs(ys.astype(np.float64) - y_o.astype(np.float64)) <= value_tolerance(g.dtype, cond, GPU_ULPS))
+    # (b) shard invariance: evaluating 8 contiguous shards gives the same bits as one launch
+    from adaptive_interpolation_b200 import sharding
+    y2 = torch.empty_like(x)
+    for lo, hi in sharding.shard_bounds(n, 8):
+        tab.eval_ptr(x.data_ptr() + lo * x.element_size(), y2.data_ptr() + lo * x.element_size(), hi - lo, s)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int32 if tdt == torch.float32 else torch.int64),
+                       y2.view(torch.int32 if tdt == torch.float32 else torch.int64))
+    del y2
+    # (c) linearity in the coefficients: doubling every coefficient doubles y exactly
+    f2 = tables.FlatTable(f.basis, f.order, f.dtype, f.breaks, f.coef * 2)
+    tab2 = tables.DeviceTable(f2, 0)
+    y3 = torch.empty_like(x)
+    tab2.eval_ptr(x.data_ptr(), y3.data_ptr(), n, s)
+    torch.cuda.synchronize()
+    assert torch.equal(y3, y * 2)
+    del y3
+    # (d) sortedness: leaf ordinals of sorted points are non-decreasing and hit both end leaves
+    m = 1 << 24
+    xs_sorted, _ = torch.sort(x[:m])
+    idx = torch.empty(m, dtype=torch.int32, device="cuda")
+    tab.index_ptr(xs_sorted.data_ptr(), idx.data_ptr(), m, s)
+    torch.cuda.synchronize()
+    assert bool((idx[1:] >= idx[:-1]).all()) and int(idx[0]) == 0 and int(idx[-1]) == f.n_leaves - 1
+    # (e) every leaf boundary is honoured: x in [breaks[i], breaks[i+1]) for the chosen leaf
+    br = to_dev(f.breaks)
+    li = idx.long()
+    assert bool((xs_sorted >= br[li]).all()) and bool((xs_sorted < br[li + 1]).all())

@@ -1,0 +1,54 @@
+"""The N>1 host path on CPU: two gloo ranks shard one array contiguously, evaluate their shard
+(with the oracle standing in for the device), and reduce the timing scalar with MAX -- the same
+bookkeeping bench.py does under torchrun with NCCL.  No data-path collective exists."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+from conftest import ROOT
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import numpy as np
+    import torch.distributed as dist
+    from adaptive_interpolation_b200 import sharding, tables
+    from oracle import oracle_np
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
+                            rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = tables.load_golden("approx__64o7-p1.19209289551e-06")
+    f = tables.flatten(g)
+    n = 100003
+    x = np.random.default_rng(7).uniform(0, 20, n)
+    lo, hi = sharding.shard_of(n, rank, world)
+    y_local = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x[lo:hi])
+    t = sharding.max_over_ranks(1.0 + rank, dist)
+    pts = sharding.sum_over_ranks(hi - lo, dist)
+    assert t == float(world), t
+    assert pts == n, pts
+    y_full = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x)
+    assert np.array_equal(y_local, y_full[lo:hi])
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok", lo, hi)
+""") % ROOT
+
+
+@pytest.mark.timeout(180)
+def test_two_gloo_ranks(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", PORT=port, MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=170)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
