@@ -64,16 +64,21 @@ def is_current():
         return fh.read().strip() == fingerprint()
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA translation unit for sm_100a and link the shared library."""
-    if not force and is_current():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA translation unit for sm_100a and link the shared library.
+    `defines` / `out` build a tuning variant (tools/tune.py) next to the product library."""
+    variant = out is not None
+    lib = os.path.join(LIBDIR, out) if variant else LIB
+    if not variant and not force and is_current():
         return LIB
     nvcc = nvcc_path()
-    os.makedirs(OBJDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj_" + out) if variant else OBJDIR
+    os.makedirs(objdir, exist_ok=True)
+    dflags = ["-D" + d for d in defines]
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -86,13 +91,14 @@ def build(force=False, verbose=False):
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(os.path.join(LIBDIR, "fingerprint"), "w") as fh:
-        fh.write(fingerprint())
-    return LIB
+    if not variant:
+        with open(os.path.join(LIBDIR, "fingerprint"), "w") as fh:
+            fh.write(fingerprint())
+    return lib
 
 
 if __name__ == "__main__":

@@ -60,7 +60,7 @@ int grid_budget(int dflt) {
     const char* e = std::getenv("AI_B200_MAX_CELLS");
     if (!e || !*e) return dflt;
     const long v = std::strtol(e, nullptr, 10);
-    return (v >= 1 && v < dflt) ? (int)v : dflt;
+    return (v >= 2 && v < dflt) ? (int)v : dflt;    // a domain straddling 0 needs >= 2 cells
 }
 constexpr int kHostSlots = 3;          // host pipeline depth
 
@@ -89,6 +89,7 @@ struct ai_table {
     ai::TableView view{};
     int blocks_per_sm = 1, sm_count = 1;
     int smem_resident = 1;
+    int rank_mode = 0;
     HostPipe pipe;
 };
 
@@ -101,7 +102,55 @@ struct GridPlan {
     int p = 0, K = 0, G = 0;
     long long g0 = 0;
     std::vector<uint16_t> first;
+    // rank mode (see Lookup::rank_guess): coarse cell = fine cell / q, leaf = rank in cont
+    int rank_mode = 0;
+    unsigned div_mul = 0, div_shift = 0, div_add = 0;
+    unsigned cont = 0;
 };
+
+long long gcd_ll(long long a, long long b) {
+    while (b) { const long long t = a % b; a = b; b = t; }
+    return a < 0 ? -a : a;
+}
+
+// Try to express first[] as "rank of the coarse cell in a <= 64-bit bitmap".  Everything is
+// verified exhaustively over the G fine cells; on any mismatch rank mode stays off.
+void plan_rank(const std::vector<double>& b, GridPlan* gp) {
+    if (gp->K != 0 || gp->p < 0) return;
+    const int64_t L = (int64_t)b.size() - 1;
+    const int G = gp->G;
+    long long q = 0;
+    for (int64_t k = 1; k < L; ++k) {
+        const long long off = (long long)std::ldexp(b[k], gp->p) - gp->g0;     // exact integer
+        q = gcd_ll(q, off);
+    }
+    if (q == 0) q = G;                                   // single leaf
+    const long long Gc = (G + q - 1) / q;
+    if (Gc > 32) return;
+    unsigned mul = 0, sh = 0;
+    bool found = false;
+    for (int S = 31; S >= 0 && !found; --S) {
+        const unsigned long long M = ((1ull << S) + (unsigned long long)q - 1) / (unsigned long long)q;
+        if (M == 0 || M >= (1ull << 32) || (unsigned long long)(G - 1) * M >= (1ull << 32)) continue;
+        if ((unsigned long long)(G - 1) * M + ((1ull << S) - 1) >= (1ull << 32)) continue;
+        bool ok = true;
+        for (int v = 0; v < G && ok; ++v) ok = (((unsigned)v * (unsigned)M) >> S) == (unsigned)(v / q);
+        if (ok) { mul = (unsigned)M; sh = (unsigned)S; found = true; }
+    }
+    if (!found) return;
+    unsigned cont = 0;
+    for (long long c = 1; c < Gc; ++c)
+        if (gp->first[(size_t)(c * q)] == gp->first[(size_t)((c - 1) * q)]) cont |= (1u << c);
+    const unsigned add = (unsigned)(0u - (unsigned)gp->g0 * mul);      // -g0 * mul  (mod 2^32)
+    for (int g = 0; g < G; ++g) {                        // exhaustive check of the device formula
+        const unsigned gabs = (unsigned)(gp->g0 + g);    // what Lookup::cell_abs returns
+        const unsigned c = (gabs * mul + add) >> sh;
+        const unsigned below = (c >= 31) ? ~0u : ((2u << c) - 1u);
+        const int leaf = (int)c - __builtin_popcount(cont & below);
+        if (leaf != (int)gp->first[g]) return;
+    }
+    gp->rank_mode = 1; gp->div_mul = mul; gp->div_shift = sh; gp->div_add = add; gp->cont = cont;
+}
 
 bool cells_for(const std::vector<double>& b, int p, long long* g0, long long* glast) {
     const double lo = std::ldexp(b.front(), p), hi = std::ldexp(b.back(), p);
@@ -170,6 +219,7 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
     while ((1LL << K) - 1 < maxspan) ++K;
     if (exact && K != 0) return fail(AI_ERR_TABLE, "internal: exact grid has span %lld", (long long)maxspan);
     out->K = K;
+    if (!std::getenv("AI_B200_NO_RANK")) plan_rank(b, out);     // (env: test hook for the table path)
     return AI_OK;
 }
 
@@ -183,11 +233,17 @@ int build_image(ai_table* t, const GridPlan& gp, std::vector<unsigned char>* ima
     const int hdr = (t->basis == ai::kMono) ? 0 : 2;
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
-    const int off_breaks = round_up16((size_t)gp.G * sizeof(uint16_t));
+    const int fshift = (L <= 256) ? 2 : 1;               // 8-bit entries when they fit, else 16-bit
+    const int off_breaks = round_up16((size_t)gp.G * (fshift == 2 ? 1 : 2));
     const int off_records = off_breaks + round_up16((size_t)(L + 1 + pad) * sizeof(T));
     const size_t total = (size_t)off_records + (size_t)round_up16((size_t)L * R * sizeof(T));
     image->assign(total, 0);
-    std::memcpy(image->data() + off_first, gp.first.data(), gp.first.size() * sizeof(uint16_t));
+    if (fshift == 2) {
+        for (int g = 0; g < gp.G; ++g) (*image)[off_first + g] = (unsigned char)gp.first[g];
+    } else {
+        std::memcpy(image->data() + off_first, gp.first.data(), gp.first.size() * sizeof(uint16_t));
+    }
+    t->view.first_shift = fshift;
     T* br = reinterpret_cast<T*>(image->data() + off_breaks);
     for (int64_t k = 0; k <= L; ++k) br[k] = (T)t->breaks[k];
     for (int k = 0; k < pad; ++k) br[L + 1 + k] = std::numeric_limits<T>::infinity();
@@ -262,6 +318,12 @@ int finish_table(ai_table* t) {
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
+    t->view.rank_mode = gp.rank_mode;
+    t->view.div_mul = gp.div_mul;
+    t->view.div_shift = gp.div_shift;
+    t->view.div_add = gp.div_add;
+    t->view.cont_mask = gp.cont;
+    t->rank_mode = gp.rank_mode;
     t->view.scale = std::ldexp(1.0, gp.p);
     t->view.lo = (double)gp.g0;
     t->view.hi = (double)(gp.g0 + gp.G - 1);
@@ -304,7 +366,7 @@ int launch_eval_t(const ai_table* t, const T* x, T* y, int64_t n, cudaStream_t s
         nvec = 0;
     }
     ai::LaunchCfg cfg;
-    const long long tile_elems = (long long)ai::kBlock * ai::kUnroll * VN;
+    const long long tile_elems = (long long)ai::kBlock * ai::Unroll<T>::value * VN;
     const long long want = (n + tile_elems - 1) / tile_elems;
     cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
     cfg.smem_bytes = t->view.image_bytes;
@@ -641,6 +703,7 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->record_stride = t->rstride;
     info->image_bytes = t->view.image_bytes;
     info->smem_resident = t->smem_resident;
+    info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : 0);
     info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;
     info->lower_bound = t->breaks.front(); info->upper_bound = t->breaks.back();
     return AI_OK;
@@ -715,9 +778,9 @@ int ai_copy_f32(const float* x, float* y, int64_t n, int device, void* stream) {
     if (n == 0) return AI_OK;
     DeviceGuard guard(device);
     if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", device);
-    cudaDeviceProp prop;
-    AI_CUDA(cudaGetDeviceProperties(&prop, device));
-    copy_kernel<float4><<<prop.multiProcessorCount * 8, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+    int sms = 0;
+    AI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    copy_kernel<float4><<<sms * 8, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n / 4);
     AI_CUDA(cudaGetLastError());
     return AI_OK;

@@ -18,8 +18,32 @@
 
 namespace ai {
 
-constexpr int kBlock = 256;        // threads per CTA
-constexpr int kUnroll = 4;         // 16-byte vectors in flight per thread per tile
+// Tuning knobs (overridable with -D for tools/tune.py; the defaults are the measured best,
+// see profiles/).
+#ifndef AI_UNROLL
+#define AI_UNROLL 4                // 16-byte vectors per thread per tile
+#endif
+#ifndef AI_MIN_BLOCKS
+#define AI_MIN_BLOCKS 1            // __launch_bounds__ second argument (register cap)
+#endif
+#ifndef AI_PREFETCH
+#define AI_PREFETCH 1              // 1: load tile k+1 before evaluating tile k
+#endif
+#ifndef AI_UNIFORM_PATH
+#define AI_UNIFORM_PATH 2          // 0: off, 1: test every tile, 2: adaptive (re-probe every 16 tiles)
+#endif
+
+#ifndef AI_BLOCK
+#define AI_BLOCK 512               // threads per CTA
+#endif
+#ifndef AI_UNROLL_F64
+#define AI_UNROLL_F64 AI_UNROLL    // unroll for the double kernels (2 points per vector)
+#endif
+
+constexpr int kBlock = AI_BLOCK;   // threads per CTA
+constexpr int kUnroll = AI_UNROLL; // 16-byte vectors in flight per thread per tile (copy kernel)
+template <typename T> struct Unroll { static constexpr int value = AI_UNROLL; };
+template <> struct Unroll<double> { static constexpr int value = AI_UNROLL_F64; };
 
 enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 
@@ -27,12 +51,17 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 struct TableView {
     const unsigned char* image;    // packed image in global memory (16-byte aligned)
     int image_bytes;               // multiple of 16
-    int off_first;                 // uint16 first[G]       : leaf holding the left edge of cell g
+    int off_first;                 // packed first[G]       : leaf holding the left edge of cell g
     int off_breaks;                // T breaks[L+1+pad]     : sorted breakpoints, +inf padded
     int off_records;               // T rec[L][R]           : [a, 2/(b-a), c0..cn, pad]
     int n_leaves;                  // L
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
+    int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit
+    int rank_mode;                 // 1: leaf = rank in cont_mask of the coarse cell (no table read)
+    unsigned div_mul, div_shift;   // coarse cell = (fine cell * div_mul) >> div_shift  (exact / q)
+    unsigned div_add;              // -g0 * div_mul (mod 2^32): folds the "- g0" into the multiply
+    unsigned cont_mask;            // bit c set: coarse cell c continues the leaf of cell c-1 (<= 32 cells)
     double scale;                  // 2^p (exact in T)
     double lo, hi;                 // g0 and g0+G-1 as floating point (exact in T)
     double inv_order;              // T(1./n) widened: the Legendre-like recurrence's divisor
@@ -69,46 +98,75 @@ __device__ __forceinline__ int cell_of(double x, double scale, int glo, int ghi)
 template <typename T> struct Lookup {
     T scale, lo, hi;
     int g0, ghi, kstep, lmax;
-    const uint16_t* first;
+    int fshift, rank_mode;
+    unsigned div_mul, div_shift, div_add, cont;
+    const unsigned* first;         // packed 8- or 16-bit entries, read as 32-bit words
     const T* breaks;
 
     __device__ __forceinline__ void init(const TableView& tv, const unsigned char* smem) {
         scale = (T)tv.scale; lo = (T)tv.lo; hi = (T)tv.hi;
         g0 = tv.g0; ghi = (int)tv.hi; kstep = tv.kstep; lmax = tv.n_leaves - 1;
-        first = reinterpret_cast<const uint16_t*>(smem + tv.off_first);
+        fshift = tv.first_shift; rank_mode = tv.rank_mode;
+        div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
+        first = reinterpret_cast<const unsigned*>(smem + tv.off_first);
         breaks = reinterpret_cast<const T*>(smem + tv.off_breaks);
     }
-    // grid guess: the leaf holding the left edge of x's cell.  Exact answer when kstep == 0.
-    __device__ __forceinline__ int guess(T x) const {
-        int g;
+    // fine cell of x relative to the first cell, clamped to [0, G)
+    __device__ __forceinline__ int cell(T x) const {
+        if constexpr (sizeof(T) == 4) return cell_of(x, scale, lo, hi, g0);
+        else return cell_of(x, scale, g0, ghi);
+    }
+    // leaf holding the left edge of fine cell g, from the packed table in shared memory.
+    // Entries are bytes when L <= 256 (4 per 32-bit word: 80 cells = 20 words, conflict-free).
+    __device__ __forceinline__ int table_guess(int g) const {
+        const unsigned w = first[g >> fshift];
+        const int sub = g & ((1 << fshift) - 1);
+        const int bits = 32 >> fshift;                       // 8 or 16
+        return (int)((w >> (sub * bits)) & ((1u << bits) - 1u));
+    }
+    // absolute fine cell of x, clamped to [g0, g0+G)
+    __device__ __forceinline__ unsigned cell_abs(T x) const {
         if constexpr (sizeof(T) == 4) {
-            g = cell_of(x, scale, lo, hi, g0);
+            float u = x * scale;
+            u = fmaxf(fminf(u, hi), lo);
+            return (unsigned)__float2int_rd(u);
         } else {
-            g = cell_of(x, scale, g0, ghi);
+            const int gi = __double2int_rd(x * scale);
+            return (unsigned)min(max(gi, g0), ghi);
         }
-        return first[g];
+    }
+    // dyadic tables with <= 32 coarse cells: no memory access at all.  The coarse cell is the
+    // fine cell divided by the odd factor q of the leaf width (exact multiply-shift, verified on
+    // the host for every fine cell); the leaf is the number of leaf starts at or before it.
+    __device__ __forceinline__ int rank_guess(T x) const {
+        const unsigned c = (cell_abs(x) * div_mul + div_add) >> div_shift;
+        const unsigned below = (2u << c) - 1u;
+        return (int)c - __popc(cont & below);
     }
     // one step of the branch-free forward binary search (step s = 2^k); breaks[] is +inf padded
     __device__ __forceinline__ int refine(T x, int i, int s) const {
         const int j = i + s;
         return !(x < breaks[j]) ? j : i;
     }
-    __device__ __forceinline__ int finish(int i) const { return min(i, lmax); }
 
-    // leaf ordinals of N points held in registers.  The search loop runs over steps on the
-    // outside and points on the inside, so the N dependent chains interleave (ILP) and the
-    // only branch is the warp-uniform trip count.
+    // leaf ordinals of N points held in registers.  Mode branches are warp-uniform and sit
+    // OUTSIDE the per-point loops, so the N dependent chains interleave (ILP).
     template <int N>
     __device__ __forceinline__ void leaves(const T (&x)[N], int (&i)[N]) const {
+        if (rank_mode) {
 #pragma unroll
-        for (int e = 0; e < N; ++e) i[e] = guess(x[e]);
+            for (int e = 0; e < N; ++e) i[e] = rank_guess(x[e]);
+            return;
+        }
+#pragma unroll
+        for (int e = 0; e < N; ++e) i[e] = table_guess(cell(x[e]));
         if (kstep) {                      // tables whose breakpoints are off the grid
             for (int s = kstep; s; s >>= 1) {
 #pragma unroll
                 for (int e = 0; e < N; ++e) i[e] = refine(x[e], i[e], s);
             }
 #pragma unroll
-            for (int e = 0; e < N; ++e) i[e] = finish(i[e]);
+            for (int e = 0; e < N; ++e) i[e] = min(i[e], lmax);
         }
     }
     __device__ __forceinline__ int leaf(T x) const {
@@ -129,17 +187,30 @@ template <typename T> struct Lookup {
 // rec points at the leaf record in shared memory.  Arithmetic follows the reference's operation
 // order (adapt.py:97-139 as called from approximator.py:291-295) with each multiply-add pair
 // fused; see DESIGN.md "numerics" for the measured deviation from the reference evaluator.
+template <int BASIS, int ORDER, typename T> struct Record {
+    static constexpr int HDR = (BASIS == kMono) ? 0 : 2;
+    static constexpr int N = ORDER + 1 + HDR;
+    T v[N];                                    // [a, 2/(b-a), c0..cn]  (monomial: [c0..cn])
+    __device__ __forceinline__ void load(const T* __restrict__ rec) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = rec[k];
+    }
+};
+
+// rec holds one leaf record.  Arithmetic follows the reference's operation order (adapt.py:97-139
+// as called from approximator.py:291-295) with each multiply-add pair fused; see DESIGN.md
+// "numerics" for the measured deviation from the reference evaluator.
 template <int BASIS, int ORDER, typename T>
-__device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order) {
+__device__ __forceinline__ T eval_record(const Record<BASIS, ORDER, T>& r, T x, T inv_order) {
     if constexpr (BASIS == kMono) {
         // adapt.py:139 sum c_i x^i on the RAW x; Horner as generate.py:48-52
-        T acc = rec[ORDER];
+        T acc = r.v[ORDER];
 #pragma unroll
-        for (int j = ORDER - 1; j >= 0; --j) acc = fma_(acc, x, rec[j]);
+        for (int j = ORDER - 1; j >= 0; --j) acc = fma_(acc, x, r.v[j]);
         return acc;
     } else {
-        const T a = rec[0], s = rec[1];
-        const T* c = rec + 2;
+        const T a = r.v[0], s = r.v[1];
+        const T* c = r.v + 2;
         // adapt.py:130  xscaled = 2*(x-a)/(b-a) - 1, with 2/(b-a) precomputed per leaf in T
         const T t = fma_(x - a, s, (T)-1);
         if constexpr (ORDER == 0) {
@@ -174,6 +245,13 @@ __device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_ord
     }
 }
 
+template <int BASIS, int ORDER, typename T>
+__device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order) {
+    Record<BASIS, ORDER, T> r;
+    r.load(rec);
+    return eval_record<BASIS, ORDER, T>(r, x, inv_order);
+}
+
 // ------------------------------------------------------------------------- streaming access
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
@@ -191,7 +269,7 @@ __device__ __forceinline__ void stage_image(const TableView& tv, unsigned char* 
 // then a scalar tail.  head/tail are < Vec::N elements unless x and y are misaligned relative
 // to each other, in which case head == n and everything takes the scalar loop.
 template <int BASIS, int ORDER, typename T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, AI_MIN_BLOCKS)
 eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
             long long n, long long head, long long nvec) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -213,14 +291,33 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
     const V* __restrict__ xv = reinterpret_cast<const V*>(x + head);
     V* __restrict__ yv = reinterpret_cast<V*>(y + head);
 
+    constexpr int kUnroll = Unroll<T>::value;                      // shadows the namespace constant
     constexpr long long kTile = (long long)kBlock * kUnroll;       // vectors per tile
     constexpr int NE = kUnroll * VN;                               // points per thread per tile
     const long long full_tiles = nvec / kTile;
-    for (long long tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
+
+    auto load_tile = [&](V (&buf)[kUnroll], long long tile) {
         const long long base = tile * kTile + threadIdx.x;
-        V in[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) in[u] = ld_stream(xv + base + (long long)u * kBlock);
+        for (int u = 0; u < kUnroll; ++u) buf[u] = ld_stream(xv + base + (long long)u * kBlock);
+    };
+
+    [[maybe_unused]] int probe = 0;          // AI_UNIFORM_PATH == 2: tiles until the next probe
+    [[maybe_unused]] bool expect_uniform = true;
+    long long tile = blockIdx.x;
+    V in[kUnroll];
+#if AI_PREFETCH
+    if (tile < full_tiles) load_tile(in, tile);
+#endif
+    for (; tile < full_tiles; tile += gridDim.x) {
+#if AI_PREFETCH
+        V nxt[kUnroll];
+        const long long next = tile + gridDim.x;
+        if (next < full_tiles) load_tile(nxt, next);
+#else
+        load_tile(in, tile);
+#endif
+        const long long base = tile * kTile + threadIdx.x;
         T xs[NE];
         int li[NE];
 #pragma unroll
@@ -232,8 +329,37 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
             }
         }
         lk.template leaves<NE>(xs, li);
+        // Sorted / clustered inputs: all NE points of this thread usually sit in one leaf.  When
+        // that holds for every lane of the warp, load the record ONCE into registers (n+3 shared
+        // loads per NE points instead of per point).  Same arithmetic, so the bits are the same.
+        bool uniform = false;
+#if AI_UNIFORM_PATH == 1
+        {
+            bool same = true;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T>(records + li[e] * R, xs[e], inv_order);
+            for (int e = 1; e < NE; ++e) same = same && (li[e] == li[0]);
+            uniform = __all_sync(0xffffffffu, same);
+        }
+#elif AI_UNIFORM_PATH == 2
+        if (expect_uniform || probe == 0) {
+            bool same = true;
+#pragma unroll
+            for (int e = 1; e < NE; ++e) same = same && (li[e] == li[0]);
+            uniform = __all_sync(0xffffffffu, same);
+            expect_uniform = uniform;
+            probe = 16;
+        }
+        --probe;
+#endif
+        if (uniform) {
+            Record<BASIS, ORDER, T> rec;
+            rec.load(records + li[0] * R);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+        } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T>(records + li[e] * R, xs[e], inv_order);
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             V out;
@@ -244,6 +370,10 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
             }
             st_stream(yv + base + (long long)u * kBlock, out);
         }
+#if AI_PREFETCH
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) in[u] = nxt[u];
+#endif
     }
     // remainder vectors (less than one tile), spread over the whole grid
     const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;

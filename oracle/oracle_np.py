@@ -68,6 +68,56 @@ def basis_values(basis, order, dtype, x, a, b):
     return B
 
 
+def basis_derivatives(basis, order, t):
+    """dB_i/dt in float64 (differentiated recurrences); zero for the monomial basis, whose
+    argument is the raw x and carries no rescale rounding."""
+    n = int(order)
+    t = np.asarray(t, dtype=np.float64)
+    B = [np.ones_like(t), t]
+    D = [np.zeros_like(t), np.ones_like(t)]
+    if basis == "monomial":
+        return [np.zeros_like(t) for _ in range(n + 1)]
+    for i in range(2, n + 1):
+        if basis == "chebyshev":
+            B.append(2 * t * B[i - 1] - B[i - 2])
+            D.append(2 * B[i - 1] + 2 * t * D[i - 1] - D[i - 2])
+        else:
+            B.append(((2 * i - 1) * t * B[i - 1] + (i - 1) * B[i - 2]) / n)
+            D.append(((2 * i - 1) * (B[i - 1] + t * D[i - 1]) + (i - 1) * D[i - 2]) / n)
+    return D[:n + 1]
+
+
+def error_scale(breaks, coef, basis, order, x):
+    """The scale (per point, float64) on which two correct evaluators may differ by O(eps):
+         sum_i |c_i B_i(t)|            rounding inside the recurrence and the dot product
+       + (1 + |t|) * sum_i |c_i B_i'(t)|   the rescaled argument t itself is only known to
+                                           ~eps*(1+|t|): 2*(x-a)/(b-a)-1 (adapt.py:130) and
+                                           (2./(b-a))*(x-a)-1 (generate.py:83) round differently
+    For Chebyshev fits of J0 the first term alone vanishes at zeros of the function sitting at a
+    leaf centre while the second does not; max|f| (the reference tests' scale,
+    tests/generate_tests.py:27) is an upper-bound proxy for their sum."""
+    breaks = np.asarray(breaks)
+    dt = breaks.dtype.type
+    n = int(order)
+    coef = np.asarray(coef, dtype=dt).reshape(len(breaks) - 1, n + 1).astype(np.float64)
+    x = np.asarray(x, dtype=dt)
+    idx = leaf_index(breaks, x)
+    a, b = breaks[idx].astype(np.float64), breaks[idx + 1].astype(np.float64)
+    xx = x.astype(np.float64)
+    with np.errstate(all="ignore"):
+        if basis == "monomial":
+            B = [xx ** i for i in range(n + 1)]
+            D = [np.zeros_like(xx)] * (n + 1)
+            t = np.zeros_like(xx)
+        else:
+            t = 2 * (xx - a) / (b - a) - 1
+            B = [b_.astype(np.float64) for b_ in basis_values(basis, n, np.float64, t * 0 + xx, a, b)]
+            D = basis_derivatives(basis, n, t)
+        s0 = sum(np.abs(coef[idx, i] * B[i]) for i in range(n + 1))
+        s1 = sum(np.abs(coef[idx, i] * D[i]) for i in range(n + 1))
+        return s0 + (1 + np.abs(t)) * s1
+
+
 def evaluate(breaks, coef, basis, order, x, want_cond=False):
     """y (and optionally idx, cond) for a flattened table.  coef has shape [L, order+1]."""
     breaks = np.asarray(breaks)

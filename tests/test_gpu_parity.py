@@ -3,9 +3,13 @@
 Bar (BASELINE.json north_star): leaf indices bit-exact with the reference's BST walk; values
 within a few ulp of the reference CPU evaluation and inside the interpolant's error bound.
 
-"ulp" here is eps * sum_i |c_i B_i(x)| -- the magnitude every evaluation order's rounding errors
-live on (for a Chebyshev series it is ~ max|f|; J0 has zeros, so ulps of y itself would be
-meaningless there -- SURVEY.md section 7 "value tolerance").
+"ulp" here is eps * oracle_np.error_scale(x) = eps * (sum_i |c_i B_i(t)| + (1+|t|) sum_i |c_i B_i'(t)|):
+the first term is where the rounding errors of any evaluation order live, the second is the
+first-order effect of the rescaled argument t being known only to eps*(1+|t|) (the reference's
+Python evaluator and its generated kernel already round t differently: adapt.py:130 vs
+generate.py:83).  J0 has zeros, so ulps of y itself would be meaningless.
+Measured on this scale: the reference's own generated kernel deviates from its Python evaluator
+by up to 1.5 units over the golden points; the GPU is held to GPU_ULPS = 4.
 """
 import ctypes
 import json
@@ -26,10 +30,8 @@ pytestmark = pytest.mark.gpu
 
 NAMES = all_golden_names()
 SAVED = [n for n in NAMES if n.startswith("approx")]
-# GPU (fused multiply-add, precomputed 2/(b-a)) vs the reference's Python evaluator.
-# The reference's own generated kernel differs from its Python evaluator by up to 8.3 of these
-# units (tests/test_oracle.py::test_reference_generated_kernel); we hold the GPU to 12.
-GPU_ULPS = 12
+# GPU (fused multiply-add, precomputed 2/(b-a)) vs the reference's Python evaluator
+GPU_ULPS = 4
 REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
 
 
@@ -76,7 +78,8 @@ def test_values_vs_reference(name):
     g = golden(name)
     tab = dev_table(name)
     y = gpu_eval(tab, g.x)
-    _, _, cond = oracle.c_eval_tree(g.tree_1d, g.max_order, g.num_levels, g.basis, g.x)
+    f = tables.flatten(g)
+    cond = oracle_np.error_scale(f.breaks, f.coef, f.basis, f.order, g.x)
     fin = np.isfinite(g.y_ref) & np.isfinite(cond)
     assert np.all(~np.isfinite(y[~np.isfinite(g.y_ref)]))        # inf / nan inputs stay non-finite
     err = np.abs(y[fin].astype(np.float64) - g.y_ref[fin].astype(np.float64))
@@ -128,7 +131,7 @@ def test_index_adversarial_neighbourhoods(name):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("cells", [1, 7, 64])
+@pytest.mark.parametrize("cells", [2, 7, 64])
 def test_index_exact_in_forced_search_mode(name, cells, monkeypatch):
     """Cap the grid so that the bounded binary search does the work on every table."""
     monkeypatch.setenv("AI_B200_MAX_CELLS", str(cells))
@@ -143,6 +146,28 @@ def test_index_exact_in_forced_search_mode(name, cells, monkeypatch):
     monkeypatch.delenv("AI_B200_MAX_CELLS")
     y0 = gpu_eval(dev_table(name), g.x)
     assert np.array_equal(y, y0, equal_nan=True)                  # same leaf -> same arithmetic
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
+    """Small dyadic tables normally resolve the leaf with the in-register bitmap rank
+    (lookup_mode 2); force the packed first[] table path on them and require identical bits."""
+    g = golden(name)
+    tab_default = dev_table(name)
+    monkeypatch.setenv("AI_B200_NO_RANK", "1")
+    tab = dev_table(name)
+    assert tab.info()["lookup_mode"] in (0, 1)
+    assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
+    assert np.array_equal(gpu_eval(tab, g.x), gpu_eval(tab_default, g.x), equal_nan=True)
+
+
+def test_lookup_modes_of_saved_tables():
+    modes = {name: dev_table(name).info()["lookup_mode"] for name in NAMES}
+    report(test="lookup_modes", modes=modes)
+    # BASELINE config 2's table (15 leaves, 16 coarse cells) must take the register-only path
+    assert modes["approx__32o6-p1.19209289551e-06"] == 2
+    assert modes["gen__cfg3_j0_cheb_o13_f64"] == 2
+    assert modes["gen__cfg4_f1_leg_o7_f64"] == 1
 
 
 def test_saved_tables_need_no_search():
@@ -167,7 +192,8 @@ def test_million_points_vs_oracle(name):
     rng = np.random.default_rng(12345)
     x = rng.uniform(float(f.breaks[0]), float(f.breaks[-1]), 1 << 20).astype(g.dtype)
     x = np.minimum(x, np.nextafter(f.breaks[-1], g.dtype(-np.inf)))
-    y_o, idx_o, cond = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x, want_cond=True)
+    y_o, idx_o, _ = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x, want_cond=True)
+    cond = oracle_np.error_scale(f.breaks, f.coef, f.basis, f.order, x)
     assert np.array_equal(gpu_index(tab, x), idx_o)
     y = gpu_eval(tab, x)
     err = np.abs(y.astype(np.float64) - y_o.astype(np.float64))
@@ -341,7 +367,8 @@ def test_full_size_properties(name, log2n):
     # (a) a strided sample of the full run agrees with the oracle
     step = n // (1 << 16)
     xs, ys = x[::step].cpu().numpy(), y[::step].cpu().numpy()
-    y_o, idx_o, cond = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, xs, want_cond=True)
+    y_o, idx_o, _ = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, xs, want_cond=True)
+    cond = oracle_np.error_scale(f.breaks, f.coef, f.basis, f.order, xs)
     assert np.all(np.abs(ys.astype(np.float64) - y_o.astype(np.float64)) <= value_tolerance(g.dtype, cond, GPU_ULPS))
     # (b) shard invariance: evaluating 8 contiguous shards gives the same bits as one launch
     from adaptive_interpolation_b200 import sharding

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Build tuning variants of libai_b200.so (compile-time knobs of csrc/ai_kernels.cuh) here, then
+sweep them on the GPU box:
+
+    python tools/tune.py build                 # in the container: writes _lib/variant_*.so
+    python tools/tune.py run [--tables ...]    # on the GPU: runs tools/sweep.py per variant
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+VARIANTS = {
+    # tag: defines
+    "u4_p1_c2": ["AI_UNROLL=4", "AI_PREFETCH=1", "AI_UNIFORM_PATH=2"],
+    "u4_p1_c0": ["AI_UNROLL=4", "AI_PREFETCH=1", "AI_UNIFORM_PATH=0"],
+    "u4_p1_c1": ["AI_UNROLL=4", "AI_PREFETCH=1", "AI_UNIFORM_PATH=1"],
+    "u4d8_p1_c2": ["AI_UNROLL=4", "AI_UNROLL_F64=8", "AI_PREFETCH=1", "AI_UNIFORM_PATH=2"],
+    "u4_p1_c2_t512": ["AI_UNROLL=4", "AI_PREFETCH=1", "AI_UNIFORM_PATH=2", "AI_BLOCK=512"],
+    "u4_p1_c2_t128": ["AI_UNROLL=4", "AI_PREFETCH=1", "AI_UNIFORM_PATH=2", "AI_BLOCK=128"],
+    "u4_p1_c2_b3": ["AI_UNROLL=4", "AI_PREFETCH=1", "AI_UNIFORM_PATH=2", "AI_MIN_BLOCKS=3"],
+    "u3_p1_c2": ["AI_UNROLL=3", "AI_PREFETCH=1", "AI_UNIFORM_PATH=2"],
+}
+TABLES = ("approx__32o6-p1.19209289551e-06,approx__32o13-p1.19209289551e-06,gen__cfg3_j0_cheb_o13_f64,"
+          "approx__64o7-p2.22044604925e-14,approx__64o6-p1.19209289551e-06,approx__32o3-p1.19209289551e-06")
+
+
+def main():
+    from adaptive_interpolation_b200 import build
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "build"
+    if cmd == "build":
+        for tag, defs in VARIANTS.items():
+            print(tag, build.build(defines=defs, out="variant_%s.so" % tag))
+        return
+    tables = TABLES
+    if "--tables" in sys.argv:
+        tables = sys.argv[sys.argv.index("--tables") + 1]
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else list(VARIANTS)
+    for tag in only:
+        lib = os.path.join(ROOT, "adaptive_interpolation_b200", "_lib", "variant_%s.so" % tag)
+        if not os.path.exists(lib):
+            continue
+        env = dict(os.environ, AI_B200_LIB=lib)
+        print("=== variant", tag, VARIANTS.get(tag), flush=True)
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "--tables", tables,
+                        "--tag", "tune_" + tag, "--reps", "15"], env=env)
+
+
+if __name__ == "__main__":
+    main()
