@@ -21,7 +21,7 @@ namespace ai {
 // Tuning knobs (overridable with -D for tools/tune.py; the defaults are the measured best,
 // see profiles/).
 #ifndef AI_UNROLL
-#define AI_UNROLL 4                // 16-byte vectors per thread per tile
+#define AI_UNROLL 6                // 16-byte vectors per thread per tile (float: 24 points)
 #endif
 #ifndef AI_MIN_BLOCKS
 #define AI_MIN_BLOCKS 1            // __launch_bounds__ second argument (register cap)
@@ -37,7 +37,7 @@ namespace ai {
 #define AI_BLOCK 512               // threads per CTA
 #endif
 #ifndef AI_UNROLL_F64
-#define AI_UNROLL_F64 AI_UNROLL    // unroll for the double kernels (2 points per vector)
+#define AI_UNROLL_F64 5            // unroll for the double kernels (2 points per vector: 10 points)
 #endif
 
 constexpr int kBlock = AI_BLOCK;   // threads per CTA
