@@ -90,6 +90,9 @@ struct ai_table {
     int blocks_per_sm = 1, sm_count = 1;
     int smem_resident = 1;
     int rank_mode = 0;
+    int mode = ai::kSmem;              // table residency: kSmem / kSmemBank / kGlobal
+    int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
+    int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     HostPipe pipe;
 };
 
@@ -259,22 +262,23 @@ int build_image(ai_table* t, const GridPlan& gp, std::vector<unsigned char>* ima
     }
     t->rstride = R;
     t->view.image_bytes = (int)total;
+    t->view.n_records_elems = (int)(L * R);
     t->view.off_first = off_first;
     t->view.off_breaks = off_breaks;
     t->view.off_records = off_records;
     return AI_OK;
 }
 
-int prepare_dispatch(int basis, int dtype, int order, int smem, int* bps) {
+int prepare_dispatch(int basis, int dtype, int order, int mode, int smem, int* bps) {
     cudaError_t e = cudaErrorInvalidValue;
     if (dtype == AI_DTYPE_F32) {
-        if (basis == ai::kCheb) e = ai::prepare_cheb_f32(order, smem, bps);
-        else if (basis == ai::kLeg) e = ai::prepare_leg_f32(order, smem, bps);
-        else e = ai::prepare_mono_f32(order, smem, bps);
+        if (basis == ai::kCheb) e = ai::prepare_cheb_f32(order, mode, smem, bps);
+        else if (basis == ai::kLeg) e = ai::prepare_leg_f32(order, mode, smem, bps);
+        else e = ai::prepare_mono_f32(order, mode, smem, bps);
     } else {
-        if (basis == ai::kCheb) e = ai::prepare_cheb_f64(order, smem, bps);
-        else if (basis == ai::kLeg) e = ai::prepare_leg_f64(order, smem, bps);
-        else e = ai::prepare_mono_f64(order, smem, bps);
+        if (basis == ai::kCheb) e = ai::prepare_cheb_f64(order, mode, smem, bps);
+        else if (basis == ai::kLeg) e = ai::prepare_leg_f64(order, mode, smem, bps);
+        else e = ai::prepare_mono_f64(order, mode, smem, bps);
     }
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "kernel prepare failed: %s", cudaGetErrorString(e));
     return AI_OK;
@@ -308,9 +312,26 @@ int finish_table(ai_table* t) {
         return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
                     t->device, prop.major, prop.minor);
     t->sm_count = prop.multiProcessorCount;
-    if ((size_t)t->view.image_bytes > (size_t)prop.sharedMemPerBlockOptin)
-        return fail(AI_ERR_UNSUPPORTED, "table image (%d B) exceeds shared memory per CTA (%zu B); "
-                    "the L2-resident path is not built yet", t->view.image_bytes, (size_t)prop.sharedMemPerBlockOptin);
+    // ---- table residency -------------------------------------------------------------------
+    const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
+    const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
+    const int copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
+    const size_t bank_bytes = (size_t)t->view.off_records + (size_t)L * t->rstride * esz * copies;
+    // leaves a warp can address without two of them sharing a bank (odd record stride)
+    const int64_t conflict_free_leaves = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
+    int mode = ai::kSmem;
+    if ((size_t)t->view.image_bytes > smem_cap) mode = ai::kGlobal;
+    else if (L > conflict_free_leaves && bank_bytes <= smem_cap) mode = ai::kSmemBank;
+    if (const char* e = std::getenv("AI_B200_FORCE_MODE")) {           // test hook
+        const int m = std::atoi(e);
+        if (m == ai::kGlobal) mode = ai::kGlobal;
+        else if (m == ai::kSmem && (size_t)t->view.image_bytes <= smem_cap) mode = ai::kSmem;
+        else if (m == ai::kSmemBank && bank_bytes <= smem_cap) mode = ai::kSmemBank;
+    }
+    t->mode = mode;
+    t->smem_resident = (mode != ai::kGlobal);
+    t->eval_smem = (mode == ai::kGlobal) ? 0 : (mode == ai::kSmemBank ? (int)bank_bytes : t->view.image_bytes);
+    t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
     AI_CUDA(cudaMalloc(&t->d_image, image.size()));
     AI_CUDA(cudaMemcpy(t->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
 
@@ -332,9 +353,14 @@ int finish_table(ai_table* t) {
     t->view.inv_order = (t->dtype == AI_DTYPE_F32) ? (double)(float)inv : inv;
 
     int bps = 0;
-    rc = prepare_dispatch(t->basis, t->dtype, t->order, t->view.image_bytes, &bps);
+    rc = prepare_dispatch(t->basis, t->dtype, t->order, t->mode, t->eval_smem, &bps);
     if (rc) return rc;
-    if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->view.image_bytes);
+    if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->eval_smem);
+    if (t->mode != ai::kGlobal && t->aux_smem > 48 * 1024) {
+        int dummy = 0;      // opt the reduction kernel (packed layout) into large shared memory too
+        rc = prepare_dispatch(t->basis, t->dtype, t->order, ai::kSmem, t->aux_smem, &dummy);
+        if (rc) return rc;
+    }
     t->blocks_per_sm = bps;
     return AI_OK;
 }
@@ -369,17 +395,18 @@ int launch_eval_t(const ai_table* t, const T* x, T* y, int64_t n, cudaStream_t s
     const long long tile_elems = (long long)ai::kBlock * ai::Unroll<T>::value * VN;
     const long long want = (n + tile_elems - 1) / tile_elems;
     cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
-    cfg.smem_bytes = t->view.image_bytes;
+    cfg.smem_bytes = t->eval_smem;
     cfg.stream = stream;
     cudaError_t e;
+    const int m = t->mode;
     if constexpr (sizeof(T) == 4) {
-        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f32(t->order, cfg, t->view, x, y, n, head, nvec);
-        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f32(t->order, cfg, t->view, x, y, n, head, nvec);
-        else e = ai::launch_eval_mono_f32(t->order, cfg, t->view, x, y, n, head, nvec);
+        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f32(t->order, m, cfg, t->view, x, y, n, head, nvec);
+        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f32(t->order, m, cfg, t->view, x, y, n, head, nvec);
+        else e = ai::launch_eval_mono_f32(t->order, m, cfg, t->view, x, y, n, head, nvec);
     } else {
-        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f64(t->order, cfg, t->view, x, y, n, head, nvec);
-        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f64(t->order, cfg, t->view, x, y, n, head, nvec);
-        else e = ai::launch_eval_mono_f64(t->order, cfg, t->view, x, y, n, head, nvec);
+        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f64(t->order, m, cfg, t->view, x, y, n, head, nvec);
+        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f64(t->order, m, cfg, t->view, x, y, n, head, nvec);
+        else e = ai::launch_eval_mono_f64(t->order, m, cfg, t->view, x, y, n, head, nvec);
     }
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));
     return AI_OK;
@@ -407,11 +434,15 @@ int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* st
     if (!x || !idx) return fail(AI_ERR_INVALID, "x or idx is NULL");
     DeviceGuard guard(t->device);
     if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
-    if (t->view.image_bytes > 48 * 1024)
-        AI_CUDA(cudaFuncSetAttribute(ai::index_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->view.image_bytes));
     const long long want = (n + ai::kBlock - 1) / ai::kBlock;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * 4));
-    ai::index_kernel<T><<<grid, ai::kBlock, t->view.image_bytes, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * 2));
+    if (t->mode == ai::kGlobal) {
+        ai::index_kernel<T, ai::kGlobal><<<grid, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
+    } else {
+        if (t->aux_smem > 48 * 1024)
+            AI_CUDA(cudaFuncSetAttribute(ai::index_kernel<T, ai::kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->aux_smem));
+        ai::index_kernel<T, ai::kSmem><<<grid, ai::kBlock, t->aux_smem, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
+    }
     AI_CUDA(cudaGetLastError());
     return AI_OK;
 }
@@ -430,17 +461,18 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     ai::LaunchCfg cfg;
     const long long want = (n + ai::kBlock - 1) / ai::kBlock;
     cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
-    cfg.smem_bytes = t->view.image_bytes;
+    cfg.smem_bytes = t->aux_smem;
     cfg.stream = s;
     cudaError_t e;
+    const int m = (t->mode == ai::kGlobal) ? ai::kGlobal : ai::kSmem;
     if constexpr (sizeof(T) == 4) {
-        if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, cfg, t->view, x, result, n);
-        else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, cfg, t->view, x, result, n);
-        else e = ai::launch_sum_mono_f32(t->order, cfg, t->view, x, result, n);
+        if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, m, cfg, t->view, x, result, n);
+        else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, m, cfg, t->view, x, result, n);
+        else e = ai::launch_sum_mono_f32(t->order, m, cfg, t->view, x, result, n);
     } else {
-        if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f64(t->order, cfg, t->view, x, result, n);
-        else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f64(t->order, cfg, t->view, x, result, n);
-        else e = ai::launch_sum_mono_f64(t->order, cfg, t->view, x, result, n);
+        if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f64(t->order, m, cfg, t->view, x, result, n);
+        else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f64(t->order, m, cfg, t->view, x, result, n);
+        else e = ai::launch_sum_mono_f64(t->order, m, cfg, t->view, x, result, n);
     }
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "sum kernel launch failed: %s", cudaGetErrorString(e));
     return AI_OK;
@@ -702,6 +734,8 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->grid_cells = t->G; info->grid_log2_scale = t->p; info->search_steps = t->K;
     info->record_stride = t->rstride;
     info->image_bytes = t->view.image_bytes;
+    info->smem_bytes = t->eval_smem;
+    info->residency = t->mode;
     info->smem_resident = t->smem_resident;
     info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : 0);
     info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;

@@ -9,48 +9,67 @@ namespace {
 
 constexpr int kMaxOrder = 16;
 
-template <int BASIS, typename T, int ORDER>
+template <int BASIS, typename T, int ORDER, int MODE>
 struct Unit {
     static cudaError_t eval(const LaunchCfg& c, const TableView& tv, const T* x, T* y,
                             long long n, long long head, long long nvec) {
-        eval_kernel<BASIS, ORDER, T><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, y, n, head, nvec);
+        eval_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, y, n, head, nvec);
         return cudaGetLastError();
     }
     static cudaError_t sum(const LaunchCfg& c, const TableView& tv, const T* x, double* r, long long n) {
-        eval_sum_kernel<BASIS, ORDER, T><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, r, n);
-        return cudaGetLastError();
+        if constexpr (MODE == kSmemBank) {
+            return cudaErrorInvalidValue;
+        } else {
+            eval_sum_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, r, n);
+            return cudaGetLastError();
+        }
     }
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
         cudaError_t e;
         if (smem_bytes > 48 * 1024) {
-            e = cudaFuncSetAttribute(eval_kernel<BASIS, ORDER, T>,
+            e = cudaFuncSetAttribute(eval_kernel<BASIS, ORDER, T, MODE>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(eval_sum_kernel<BASIS, ORDER, T>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-            if (e != cudaSuccess) return e;
+            if constexpr (MODE != kSmemBank) {
+                e = cudaFuncSetAttribute(eval_sum_kernel<BASIS, ORDER, T, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+                if (e != cudaSuccess) return e;
+            }
         }
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<BASIS, ORDER, T>,
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<BASIS, ORDER, T, MODE>,
                                                              kBlock, smem_bytes);
     }
 };
 
-// compile-time unrolled switch over the order
+// compile-time unrolled switch over (order, mode)
 template <int BASIS, typename T, int ORDER = 0>
 struct Switch {
-    template <typename... A> static cudaError_t eval(int order, A&&... a) {
-        if (order == ORDER) return Unit<BASIS, T, ORDER>::eval(a...);
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::eval(order, a...);
+    template <typename... A> static cudaError_t eval(int order, int mode, A&&... a) {
+        if (order == ORDER) {
+            if (mode == kSmem) return Unit<BASIS, T, ORDER, kSmem>::eval(a...);
+            if (mode == kSmemBank) return Unit<BASIS, T, ORDER, kSmemBank>::eval(a...);
+            if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::eval(a...);
+            return cudaErrorInvalidValue;
+        }
+        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::eval(order, mode, a...);
         else return cudaErrorInvalidValue;
     }
-    template <typename... A> static cudaError_t sum(int order, A&&... a) {
-        if (order == ORDER) return Unit<BASIS, T, ORDER>::sum(a...);
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::sum(order, a...);
+    template <typename... A> static cudaError_t sum(int order, int mode, A&&... a) {
+        if (order == ORDER) {
+            if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::sum(a...);
+            return Unit<BASIS, T, ORDER, kSmem>::sum(a...);
+        }
+        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::sum(order, mode, a...);
         else return cudaErrorInvalidValue;
     }
-    static cudaError_t prepare(int order, int smem_bytes, int* bps) {
-        if (order == ORDER) return Unit<BASIS, T, ORDER>::prepare(smem_bytes, bps);
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::prepare(order, smem_bytes, bps);
+    static cudaError_t prepare(int order, int mode, int smem_bytes, int* bps) {
+        if (order == ORDER) {
+            if (mode == kSmem) return Unit<BASIS, T, ORDER, kSmem>::prepare(smem_bytes, bps);
+            if (mode == kSmemBank) return Unit<BASIS, T, ORDER, kSmemBank>::prepare(smem_bytes, bps);
+            if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::prepare(smem_bytes, bps);
+            return cudaErrorInvalidValue;
+        }
+        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::prepare(order, mode, smem_bytes, bps);
         else return cudaErrorInvalidValue;
     }
 };
@@ -60,15 +79,15 @@ struct Switch {
 
 #define AI_DEFINE_UNIT(NAME, BASIS, T)                                                            \
     namespace ai {                                                                                \
-    cudaError_t launch_eval_##NAME(int order, const LaunchCfg& c, const TableView& tv, const T* x, \
-                                   T* y, long long n, long long head, long long nvec) {            \
-        return Switch<BASIS, T>::eval(order, c, tv, x, y, n, head, nvec);                         \
+    cudaError_t launch_eval_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv,  \
+                                   const T* x, T* y, long long n, long long head, long long nvec) { \
+        return Switch<BASIS, T>::eval(order, mode, c, tv, x, y, n, head, nvec);                   \
     }                                                                                             \
-    cudaError_t launch_sum_##NAME(int order, const LaunchCfg& c, const TableView& tv, const T* x, \
-                                  double* r, long long n) {                                       \
-        return Switch<BASIS, T>::sum(order, c, tv, x, r, n);                                      \
+    cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv,   \
+                                  const T* x, double* r, long long n) {                           \
+        return Switch<BASIS, T>::sum(order, mode, c, tv, x, r, n);                                \
     }                                                                                             \
-    cudaError_t prepare_##NAME(int order, int smem_bytes, int* bps) {                             \
-        return Switch<BASIS, T>::prepare(order, smem_bytes, bps);                                 \
+    cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* bps) {                   \
+        return Switch<BASIS, T>::prepare(order, mode, smem_bytes, bps);                           \
     }                                                                                             \
     }

@@ -47,6 +47,19 @@ template <> struct Unroll<double> { static constexpr int value = AI_UNROLL_F64; 
 
 enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 
+// Where a kernel reads the table from.
+//   kSmem      image staged once per CTA into shared memory, records packed (stride 1)
+//   kSmemBank  as kSmem, but every record element is replicated once per shared-memory bank
+//              (32 copies of a float, 16 of a double) and lane l only ever reads copy l: gathers
+//              by random leaf are conflict-free for ANY number of leaves (tables with more
+//              leaves than banks otherwise serialise 2-4x on random inputs)
+//   kGlobal    nothing staged: grid table, breakpoints and records are read through L1/L2 from
+//              the global image (tables too large for shared memory)
+enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2 };
+template <typename T, int MODE> struct Copies {
+    static constexpr int value = (MODE == kSmemBank) ? (sizeof(T) == 4 ? 32 : 16) : 1;
+};
+
 // Everything a kernel needs to know about a table; passed by value (kernel parameter space).
 struct TableView {
     const unsigned char* image;    // packed image in global memory (16-byte aligned)
@@ -55,6 +68,7 @@ struct TableView {
     int off_breaks;                // T breaks[L+1+pad]     : sorted breakpoints, +inf padded
     int off_records;               // T rec[L][R]           : [a, 2/(b-a), c0..cn, pad]
     int n_leaves;                  // L
+    int n_records_elems;           // L * R (elements in the packed record array)
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
     int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit
@@ -103,13 +117,13 @@ template <typename T> struct Lookup {
     const unsigned* first;         // packed 8- or 16-bit entries, read as 32-bit words
     const T* breaks;
 
-    __device__ __forceinline__ void init(const TableView& tv, const unsigned char* smem) {
+    __device__ __forceinline__ void init(const TableView& tv, const unsigned char* base) {
         scale = (T)tv.scale; lo = (T)tv.lo; hi = (T)tv.hi;
         g0 = tv.g0; ghi = (int)tv.hi; kstep = tv.kstep; lmax = tv.n_leaves - 1;
         fshift = tv.first_shift; rank_mode = tv.rank_mode;
         div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
-        first = reinterpret_cast<const unsigned*>(smem + tv.off_first);
-        breaks = reinterpret_cast<const T*>(smem + tv.off_breaks);
+        first = reinterpret_cast<const unsigned*>(base + tv.off_first);
+        breaks = reinterpret_cast<const T*>(base + tv.off_breaks);
     }
     // fine cell of x relative to the first cell, clamped to [0, G)
     __device__ __forceinline__ int cell(T x) const {
@@ -191,9 +205,10 @@ template <int BASIS, int ORDER, typename T> struct Record {
     static constexpr int HDR = (BASIS == kMono) ? 0 : 2;
     static constexpr int N = ORDER + 1 + HDR;
     T v[N];                                    // [a, 2/(b-a), c0..cn]  (monomial: [c0..cn])
+    template <int STRIDE = 1>
     __device__ __forceinline__ void load(const T* __restrict__ rec) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = rec[k];
+        for (int k = 0; k < N; ++k) v[k] = rec[k * STRIDE];
     }
 };
 
@@ -245,10 +260,10 @@ __device__ __forceinline__ T eval_record(const Record<BASIS, ORDER, T>& r, T x, 
     }
 }
 
-template <int BASIS, int ORDER, typename T>
+template <int BASIS, int ORDER, typename T, int STRIDE = 1>
 __device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order) {
     Record<BASIS, ORDER, T> r;
-    r.load(rec);
+    r.template load<STRIDE>(rec);
     return eval_record<BASIS, ORDER, T>(r, x, inv_order);
 }
 
@@ -256,34 +271,52 @@ __device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_ord
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
 
-// stage the packed table image into shared memory (16-byte chunks, whole CTA)
-__device__ __forceinline__ void stage_image(const TableView& tv, unsigned char* smem) {
-    const int4* src = reinterpret_cast<const int4*>(tv.image);
-    int4* dst = reinterpret_cast<int4*>(smem);
-    for (int k = threadIdx.x; k < tv.image_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
-    __syncthreads();
+// Make the table addressable for this CTA and return its base.  kSmem: copy the packed image
+// (16-byte chunks, whole CTA).  kSmemBank: copy grid table + breakpoints, then write every record
+// element once per bank.  kGlobal: nothing to do.
+template <typename T, int MODE>
+__device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
+    if constexpr (MODE == kGlobal) {
+        return tv.image;
+    } else {
+        const int4* src = reinterpret_cast<const int4*>(tv.image);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        const int head = (MODE == kSmemBank) ? tv.off_records : tv.image_bytes;
+        for (int k = threadIdx.x; k < head / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+        if constexpr (MODE == kSmemBank) {
+            constexpr int CP = Copies<T, MODE>::value;
+            const T* rsrc = reinterpret_cast<const T*>(tv.image + tv.off_records);
+            T* rdst = reinterpret_cast<T*>(smem + tv.off_records);
+            const int n = tv.n_records_elems * CP;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) rdst[k] = __ldg(rsrc + k / CP);
+        }
+        __syncthreads();
+        return smem;
+    }
 }
 
 // ------------------------------------------------------------------------- the hot kernel
 // Work split (host computes it, see launch_eval): [0, head) scalar, then nvec 16-byte vectors,
 // then a scalar tail.  head/tail are < Vec::N elements unless x and y are misaligned relative
 // to each other, in which case head == n and everything takes the scalar loop.
-template <int BASIS, int ORDER, typename T>
+template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock, AI_MIN_BLOCKS)
 eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
             long long n, long long head, long long nvec) {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_image(tv, smem);
+    const unsigned char* base = table_base<T, MODE>(tv, smem);
 
     Lookup<T> lk;
-    lk.init(tv, smem);
-    const T* records = reinterpret_cast<const T*>(smem + tv.off_records);
-    constexpr int R = rec_stride(BASIS, ORDER);
+    lk.init(tv, base);
+    constexpr int CP = Copies<T, MODE>::value;                     // copies per record element
+    constexpr int R = rec_stride(BASIS, ORDER) * CP;               // record stride in elements
+    // bank-private layout: lane l reads copy l (float) / l mod 16 (double) of every element
+    const T* records = reinterpret_cast<const T*>(base + tv.off_records) + (threadIdx.x & (CP - 1));
     const T inv_order = (T)tv.inv_order;
 
     auto f = [&](T xv) -> T {
         const int i = lk.leaf(xv);
-        return eval_leaf<BASIS, ORDER, T>(records + i * R, xv, inv_order);
+        return eval_leaf<BASIS, ORDER, T, CP>(records + i * R, xv, inv_order);
     };
 
     using V = typename Vec<T>::type;
@@ -353,12 +386,12 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 #endif
         if (uniform) {
             Record<BASIS, ORDER, T> rec;
-            rec.load(records + li[0] * R);
+            rec.template load<CP>(records + li[0] * R);
 #pragma unroll
             for (int e = 0; e < NE; ++e) xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
         } else {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T>(records + li[e] * R, xs[e], inv_order);
+            for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T, CP>(records + li[e] * R, xs[e], inv_order);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -393,14 +426,15 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 }
 
 // The reference's no-"output" variant (generate.py:284,392-394): reduce y instead of storing it.
-template <int BASIS, int ORDER, typename T>
+template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
+    static_assert(MODE != kSmemBank, "the reduction variant uses the packed layouts only");
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_image(tv, smem);
+    const unsigned char* base = table_base<T, MODE>(tv, smem);
     Lookup<T> lk;
-    lk.init(tv, smem);
-    const T* records = reinterpret_cast<const T*>(smem + tv.off_records);
+    lk.init(tv, base);
+    const T* records = reinterpret_cast<const T*>(base + tv.off_records);
     constexpr int R = rec_stride(BASIS, ORDER);
     const T inv_order = (T)tv.inv_order;
     double acc = 0.0;
@@ -426,13 +460,14 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
 
 // leaf ordinal only: the bit-exactness check and the lookup-only ablation
 // (the reference's "test first loop", generate.py:320-332)
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 index_kernel(const TableView tv, const T* __restrict__ x, int32_t* __restrict__ idx, long long n) {
+    static_assert(MODE != kSmemBank, "lookup only: records are not read");
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_image(tv, smem);
+    const unsigned char* base = table_base<T, MODE>(tv, smem);
     Lookup<T> lk;
-    lk.init(tv, smem);
+    lk.init(tv, base);
     const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long gstride = (long long)gridDim.x * kBlock;
     for (long long k = gtid; k < n; k += gstride) idx[k] = lk.leaf_nan_exact(__ldcs(x + k));
@@ -447,11 +482,11 @@ struct LaunchCfg {
 
 // One translation unit per (basis, dtype) -- see ai_inst.cuh -- each exporting:
 #define AI_DECLARE_UNIT(NAME, T)                                                                   \
-    cudaError_t launch_eval_##NAME(int order, const LaunchCfg&, const TableView&, const T*, T*,    \
-                                   long long, long long, long long);                               \
-    cudaError_t launch_sum_##NAME(int order, const LaunchCfg&, const TableView&, const T*, double*, \
-                                  long long);                                                      \
-    cudaError_t prepare_##NAME(int order, int smem_bytes, int* blocks_per_sm);
+    cudaError_t launch_eval_##NAME(int order, int mode, const LaunchCfg&, const TableView&,        \
+                                   const T*, T*, long long, long long, long long);                 \
+    cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg&, const TableView&,         \
+                                  const T*, double*, long long);                                   \
+    cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* blocks_per_sm);
 AI_DECLARE_UNIT(cheb_f32, float)
 AI_DECLARE_UNIT(cheb_f64, double)
 AI_DECLARE_UNIT(leg_f32, float)

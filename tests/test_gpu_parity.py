@@ -161,6 +161,75 @@ def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
     assert np.array_equal(gpu_eval(tab, g.x), gpu_eval(tab_default, g.x), equal_nan=True)
 
 
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
+    """Packed shared memory / bank-private shared memory / global (L2-resident): same leaf,
+    same arithmetic, so identical indices and identical value bits on every table."""
+    g = golden(name)
+    want_y = gpu_eval(dev_table(name), g.x)
+    monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
+    tab = dev_table(name)
+    info = tab.info()
+    if mode == 1 and info["residency"] != 1:
+        # 32 (16) copies of the records do not fit in 227 KB: the library keeps its own choice
+        assert info["n_leaves"] * info["record_stride"] * 128 + info["image_bytes"] > 200 * 1024
+        pytest.skip("table too large for bank-private copies")
+    assert info["residency"] == mode
+    assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
+    assert np.array_equal(gpu_eval(tab, g.x), want_y, equal_nan=True)
+
+
+def _synthetic_table(n_leaves, lo, hi, order, dtype, seed):
+    """A table the reference has no fixture for (its 5 order-3 / 2.2e-14 pickles with ~1e4-1e5
+    leaves are listed in .MISSING_LARGE_BLOBS): uniform leaves, Chebyshev fit of sin(3x) per leaf.
+    The check is against the oracle restatement, not against frozen reference outputs."""
+    from numpy.polynomial import chebyshev as C
+    breaks = np.linspace(lo, hi, n_leaves + 1).astype(dtype)
+    coef = np.empty((n_leaves, order + 1), dtype=dtype)
+    nodes = np.cos(np.pi * (np.arange(order + 1) + 0.5) / (order + 1))
+    for i in range(n_leaves):
+        a, b = float(breaks[i]), float(breaks[i + 1])
+        coef[i] = C.chebfit(nodes, np.sin(3 * (a + (nodes + 1) * (b - a) / 2)), order)
+    return tables.FlatTable("chebyshev", order, dtype, breaks, coef)
+
+
+@pytest.mark.parametrize("n_leaves,lo,hi,dtype,expect_k0", [
+    (16384, 0.0, 16.0, np.float64, True),       # dyadic: exact grid, 16-bit entries, 2.3 MB of records
+    (20000, 0.0, 10.0, np.float64, False),      # non-dyadic widths: grid + search through L2
+    (40000, -3.0, 7.0, np.float32, False),
+])
+def test_large_table_takes_the_global_path(n_leaves, lo, hi, dtype, expect_k0):
+    f = _synthetic_table(n_leaves, lo, hi, 3, dtype, 0)
+    tab = tables.DeviceTable(f, 0)
+    info = tab.info()
+    assert info["residency"] == 2 and info["smem_resident"] == 0 and info["smem_bytes"] == 0
+    assert (info["search_steps"] == 0) == expect_k0
+    rng = np.random.default_rng(11)
+    inf = dtype(np.inf)
+    x = np.concatenate([f.breaks, np.nextafter(f.breaks, -inf), np.nextafter(f.breaks, inf),
+                        rng.uniform(lo - 1, hi + 1, 1 << 18).astype(dtype),
+                        np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+    y_o, idx_o, _ = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x, want_cond=True)
+    assert np.array_equal(gpu_index(tab, x), idx_o)
+    y = gpu_eval(tab, x)
+    scale = oracle_np.error_scale(f.breaks, f.coef, f.basis, f.order, x)
+    fin = np.isfinite(y_o) & np.isfinite(scale)
+    assert np.all(np.abs(y[fin].astype(np.float64) - y_o[fin]) <= value_tolerance(dtype, scale[fin], GPU_ULPS))
+
+
+def test_residency_selection():
+    """Small tables stay packed; tables with more leaves than banks get bank-private copies."""
+    res = {name: dev_table(name).info() for name in NAMES}
+    report(test="residency", modes={k: v["residency"] for k, v in res.items()})
+    assert res["approx__32o6-p1.19209289551e-06"]["residency"] == 0           # 15 leaves, fp32
+    assert res["approx__32o3-p1.19209289551e-06"]["residency"] == 1           # 62 leaves, fp32
+    assert res["approx__64o7-p2.22044604925e-14"]["residency"] == 1           # 64 leaves, fp64
+    assert res["approx__64o6-p1.19209289551e-06"]["residency"] == 0           # 15 leaves, fp64
+    for name, info in res.items():
+        assert info["smem_bytes"] <= 227 * 1024
+
+
 def test_lookup_modes_of_saved_tables():
     modes = {name: dev_table(name).info()["lookup_mode"] for name in NAMES}
     report(test="lookup_modes", modes=modes)
@@ -175,7 +244,7 @@ def test_saved_tables_need_no_search():
     for name in SAVED:
         info = dev_table(name).info()
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["image_bytes"] <= 48 * 1024
+        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1)
     for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
         assert dev_table(name).info()["search_steps"] >= 1
 
