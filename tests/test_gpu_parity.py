@@ -396,6 +396,30 @@ def test_python_surface_matches_reference_calls():
     pickle.dumps(ap)
 
 
+def test_integration_stub_pure_ctypes():
+    """The binding INTEGRATION.md shows a reference maintainer: ctypes only, host numpy buffers,
+    the SoA arrays of run_test.py:242-246."""
+    lib = ctypes.cdll.LoadLibrary(_cabi.LIB_PATH)
+    lib.ai_last_error.restype = ctypes.c_char_p
+    g = golden("approximations__32o6-p1.19209289551e-06")
+    ap = app.Approximator.from_record(g)
+    intervals = np.ascontiguousarray(ap.intervals, dtype=ap.dtype)
+    coeff = np.ascontiguousarray(ap.coeff, dtype=ap.dtype)
+    h = ctypes.c_void_p()
+    rc = lib.ai_table_create(0, int(ap.max_order), 0, len(intervals) - 1,
+                             intervals.ctypes.data_as(ctypes.c_void_p), coeff.ctypes.data_as(ctypes.c_void_p),
+                             0, ctypes.byref(h))
+    assert rc == 0, lib.ai_last_error()
+    x = np.ascontiguousarray(g.x[np.isfinite(g.x)])
+    y = np.empty_like(x)
+    ms = ctypes.c_double()
+    rc = lib.ai_eval_host_f32(h, x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p),
+                              ctypes.c_int64(x.size), ctypes.byref(ms))
+    assert rc == 0, lib.ai_last_error()
+    assert np.array_equal(y, gpu_eval(dev_table(g.name), x)) and ms.value > 0
+    assert lib.ai_table_destroy(h) == 0
+
+
 def test_reference_parity_test_intent():
     """tests/generate_tests.py:27: ||app.evaluate(x) - run_code(x)||_inf / max|f| < 1e-12 (fp64)."""
     for name in ("gen__cossin_cheb_o10_f64", "gen__sinsin_leg_o10_f64", "gen__cfg1_sinsin_cheb_o3_f64"):
