@@ -218,6 +218,71 @@ def test_large_table_takes_the_global_path(n_leaves, lo, hi, dtype, expect_k0):
     assert np.all(np.abs(y[fin].astype(np.float64) - y_o[fin]) <= value_tolerance(dtype, scale[fin], GPU_ULPS))
 
 
+def _random_breaks(rng, dtype, kind):
+    """Sorted, strictly increasing breakpoints of assorted nastiness."""
+    L = int(rng.integers(1, 300))
+    if kind == "dyadic":                     # what the reference's bisection produces
+        lo = float(rng.integers(-50, 50))
+        width = float(rng.choice([1.0, 3.0, 20.0, 0.375, 1e3]))
+        cuts = {0.0, 1.0}
+        for _ in range(L):
+            c = sorted(cuts)
+            k = int(rng.integers(0, len(c) - 1))
+            if c[k + 1] - c[k] > 2.0 ** -18:
+                cuts.add((c[k] + c[k + 1]) / 2)
+        b = lo + width * np.array(sorted(cuts))
+    elif kind == "random":
+        lo, hi = sorted(rng.uniform(-100, 100, 2))
+        b = np.sort(rng.uniform(lo, hi + 1e-3, L + 1))
+    elif kind == "huge":                     # wide domain: negative grid exponent
+        b = np.sort(rng.uniform(-1e9, 3e9, L + 1))
+    elif kind == "tiny":                     # domain far from zero relative to its width
+        b = 1000.0 + np.sort(rng.uniform(0, 2.0 ** -6, L + 1))
+    elif kind == "clustered":                # geometric clustering around a point (config 4 style)
+        c = rng.uniform(-5, 5)
+        off = np.concatenate([-(2.0 ** -np.arange(1, L // 2 + 2)), 2.0 ** -np.arange(1, L // 2 + 2)])
+        b = np.sort(np.concatenate([[c - 3, c + 3], c + off * 2]))
+    else:
+        raise ValueError(kind)
+    b = np.unique(b.astype(dtype))
+    return b if len(b) >= 2 else np.array([0, 1], dtype=dtype)
+
+
+@pytest.mark.parametrize("kind", ["dyadic", "random", "huge", "tiny", "clustered"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lookup_exact_on_random_tables(kind, dtype):
+    """Property test of the grid planner + device lookup: for arbitrary sorted breakpoints the
+    leaf index equals the closed form of the reference's BST walk, on every breakpoint, its
+    neighbours and random points, in whichever lookup / residency mode the library picks."""
+    rng = np.random.default_rng(hash((kind, np.dtype(dtype).name)) % (2 ** 32))
+    seen = set()
+    for trial in range(12):
+        b = _random_breaks(rng, dtype, kind)
+        L = len(b) - 1
+        coef = rng.standard_normal((L, 4)).astype(dtype)
+        tab = tables.DeviceTable(tables.FlatTable("chebyshev", 3, dtype, b, coef), 0)
+        info = tab.info()
+        seen.add((info["lookup_mode"], info["residency"], info["grid_log2_scale"] < 0))
+        inf = dtype(np.inf)
+        span = float(b[-1]) - float(b[0])
+        x = np.concatenate([b, np.nextafter(b, -inf), np.nextafter(b, inf),
+                            rng.uniform(float(b[0]) - 0.1 * span, float(b[-1]) + 0.1 * span, 4096).astype(dtype),
+                            np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, np.finfo(dtype).tiny,
+                                      -np.finfo(dtype).tiny, np.finfo(dtype).max, -np.finfo(dtype).max], dtype=dtype)])
+        got = gpu_index(tab, x)
+        want = oracle_np.leaf_index(b, x)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (kind, trial, info, x[bad[:5]], got[bad[:5]], want[bad[:5]])
+        # and the values on the in-domain points agree with the oracle
+        xin = x[np.isfinite(x) & (x >= b[0]) & (x < b[-1])]
+        y = gpu_eval(tab, xin)
+        y_o = oracle_np.evaluate(b, coef, "chebyshev", 3, xin)
+        scale = oracle_np.error_scale(b, coef, "chebyshev", 3, xin)
+        ok = np.isfinite(scale)
+        assert np.all(np.abs(y[ok].astype(np.float64) - y_o[ok]) <= value_tolerance(dtype, scale[ok], GPU_ULPS))
+    report(test="random_tables", kind=kind, dtype=np.dtype(dtype).name, modes=sorted(map(list, seen)))
+
+
 def test_residency_selection():
     """Small tables stay packed; tables with more leaves than banks get bank-private copies."""
     res = {name: dev_table(name).info() for name in NAMES}
