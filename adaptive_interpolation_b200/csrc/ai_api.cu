@@ -62,13 +62,14 @@ int grid_budget(int dflt) {
     const long v = std::strtol(e, nullptr, 10);
     return (v >= 2 && v < dflt) ? (int)v : dflt;    // a domain straddling 0 needs >= 2 cells
 }
-constexpr int kHostSlots = 3;          // host pipeline depth
+constexpr int kHostSlots = 4;          // host pipeline depth (slots actually used: AI_B200_HOST_SLOTS)
 
 struct HostPipe {
     bool ready = false;
     int64_t chunk = 0;                 // elements per chunk
-    void* dx[kHostSlots] = {nullptr, nullptr, nullptr};
-    void* dy[kHostSlots] = {nullptr, nullptr, nullptr};
+    int slots = 3;
+    void* dx[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
+    void* dy[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t in_done[kHostSlots], k_done[kHostSlots], out_done[kHostSlots];
     cudaEvent_t k_start[kHostSlots];
@@ -229,10 +230,10 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
 int round_up16(size_t v) { return (int)((v + 15) & ~(size_t)15); }
 
 template <typename T>
-int build_image(ai_table* t, const GridPlan& gp, std::vector<unsigned char>* image) {
+int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector<unsigned char>* image) {
     const int n = t->order;
     const int64_t L = t->L;
-    const int R = ai::rec_stride(t->basis, n);
+    const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T)) : ai::rec_stride(t->basis, n);
     const int hdr = (t->basis == ai::kMono) ? 0 : 2;
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
@@ -300,10 +301,6 @@ int finish_table(ai_table* t) {
     if (rc) return rc;
     t->G = gp.G; t->p = gp.p; t->K = gp.K; t->g0 = gp.g0;
 
-    std::vector<unsigned char> image;
-    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, &image) : build_image<double>(t, gp, &image);
-    if (rc) return rc;
-
     DeviceGuard guard(t->device);
     if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
     cudaDeviceProp prop;
@@ -312,22 +309,32 @@ int finish_table(ai_table* t) {
         return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
                     t->device, prop.major, prop.minor);
     t->sm_count = prop.multiProcessorCount;
-    // ---- table residency -------------------------------------------------------------------
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
+
+    // build the packed (shared-memory) image first; if it cannot be staged, rebuild it in the
+    // global layout (16-byte padded records)
+    const char* force = std::getenv("AI_B200_FORCE_MODE");                // test hook
+    const int forced = force ? std::atoi(force) : -1;
+    std::vector<unsigned char> image;
+    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image) : build_image<double>(t, gp, false, &image);
+    if (rc) return rc;
+    const bool go_global = (forced == ai::kGlobal) || ((size_t)t->view.image_bytes > smem_cap);
+    if (go_global) {
+        rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image) : build_image<double>(t, gp, true, &image);
+        if (rc) return rc;
+    }
+
+    // ---- table residency -------------------------------------------------------------------
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
     const int copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
     const size_t bank_bytes = (size_t)t->view.off_records + (size_t)L * t->rstride * esz * copies;
     // leaves a warp can address without two of them sharing a bank (odd record stride)
     const int64_t conflict_free_leaves = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
     int mode = ai::kSmem;
-    if ((size_t)t->view.image_bytes > smem_cap) mode = ai::kGlobal;
+    if (go_global) mode = ai::kGlobal;
     else if (L > conflict_free_leaves && bank_bytes <= smem_cap) mode = ai::kSmemBank;
-    if (const char* e = std::getenv("AI_B200_FORCE_MODE")) {           // test hook
-        const int m = std::atoi(e);
-        if (m == ai::kGlobal) mode = ai::kGlobal;
-        else if (m == ai::kSmem && (size_t)t->view.image_bytes <= smem_cap) mode = ai::kSmem;
-        else if (m == ai::kSmemBank && bank_bytes <= smem_cap) mode = ai::kSmemBank;
-    }
+    if (!go_global && forced == ai::kSmem) mode = ai::kSmem;
+    if (!go_global && forced == ai::kSmemBank && bank_bytes <= smem_cap) mode = ai::kSmemBank;
     t->mode = mode;
     t->smem_resident = (mode != ai::kGlobal);
     t->eval_smem = (mode == ai::kGlobal) ? 0 : (mode == ai::kSmemBank ? (int)bank_bytes : t->view.image_bytes);
@@ -482,8 +489,11 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
 int pipe_init(ai_table* t, size_t elem) {
     HostPipe& p = t->pipe;
     if (p.ready) return AI_OK;
-    p.chunk = (int64_t)(32u << 20) / (int64_t)elem;          // 32 MiB per direction per slot
-    for (int s = 0; s < kHostSlots; ++s) {
+    long mib = 32;                                            // MiB per direction per slot
+    if (const char* e = std::getenv("AI_B200_HOST_CHUNK_MB")) { const long v = std::atol(e); if (v >= 1 && v <= 1024) mib = v; }
+    if (const char* e = std::getenv("AI_B200_HOST_SLOTS")) { const long v = std::atol(e); if (v >= 2 && v <= kHostSlots) p.slots = (int)v; }
+    p.chunk = (int64_t)(mib << 20) / (int64_t)elem;
+    for (int s = 0; s < p.slots; ++s) {
         AI_CUDA(cudaMalloc(&p.dx[s], (size_t)p.chunk * elem));
         AI_CUDA(cudaMalloc(&p.dy[s], (size_t)p.chunk * elem));
         AI_CUDA(cudaEventCreateWithFlags(&p.in_done[s], cudaEventDisableTiming));
@@ -501,7 +511,7 @@ int pipe_init(ai_table* t, size_t elem) {
 void pipe_destroy(ai_table* t) {
     HostPipe& p = t->pipe;
     if (!p.ready) return;
-    for (int s = 0; s < kHostSlots; ++s) {
+    for (int s = 0; s < p.slots; ++s) {
         cudaFree(p.dx[s]); cudaFree(p.dy[s]);
         cudaEventDestroy(p.in_done[s]); cudaEventDestroy(p.out_done[s]);
         cudaEventDestroy(p.k_start[s]); cudaEventDestroy(p.k_done[s]);
@@ -528,9 +538,9 @@ int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_m
     const int64_t nchunks = (n + p.chunk - 1) / p.chunk;
     double ms_total = 0.0;
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int s = (int)(c % kHostSlots);
+        const int s = (int)(c % p.slots);
         const int64_t off = c * p.chunk, m = std::min<int64_t>(p.chunk, n - off);
-        if (c >= kHostSlots) {
+        if (c >= p.slots) {
             // slot reuse: its previous D2H must have drained before we overwrite dx/dy
             AI_CUDA(cudaEventSynchronize(p.out_done[s]));
             float ms = 0.f;
@@ -549,9 +559,9 @@ int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_m
         AI_CUDA(cudaEventRecord(p.out_done[s], p.s_out));
     }
     AI_CUDA(cudaStreamSynchronize(p.s_out));
-    const int64_t first_pending = std::max<int64_t>(0, nchunks - kHostSlots);
+    const int64_t first_pending = std::max<int64_t>(0, nchunks - p.slots);
     for (int64_t c = first_pending; c < nchunks; ++c) {
-        const int s = (int)(c % kHostSlots);
+        const int s = (int)(c % p.slots);
         float ms = 0.f;
         AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
         ms_total += ms;

@@ -90,9 +90,19 @@ template <> struct Vec<float>  { using type = float4;  static constexpr int N = 
 template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
 
 template <typename T> __host__ __device__ constexpr int rec_header(int basis) { return basis == kMono ? 0 : 2; }
-// record stride in elements: odd, so that lanes on different leaves hit different banks
+// record stride in elements.  Shared-memory layouts: odd, so that lanes on different leaves hit
+// different banks.  Global (L2-resident) layout: padded to 16 bytes so that a record is fetched
+// with 128-bit loads (a random-leaf gather costs one L1 tag lookup per line per instruction).
 __host__ __device__ constexpr int rec_stride(int basis, int order) {
     return ((order + 1 + (basis == kMono ? 0 : 2)) | 1);
+}
+__host__ __device__ constexpr int rec_stride_global(int basis, int order, int elem_bytes) {
+    const int per = 16 / elem_bytes;
+    return (order + 1 + (basis == kMono ? 0 : 2) + per - 1) / per * per;
+}
+template <int BASIS, int ORDER, typename T, int MODE>
+__host__ __device__ constexpr int rec_stride_for() {
+    return MODE == kGlobal ? rec_stride_global(BASIS, ORDER, (int)sizeof(T)) : rec_stride(BASIS, ORDER);
 }
 
 __device__ __forceinline__ float  fma_(float a, float b, float c)    { return __fmaf_rn(a, b, c); }
@@ -210,6 +220,25 @@ template <int BASIS, int ORDER, typename T> struct Record {
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = rec[k * STRIDE];
     }
+    // 16-byte aligned record in global memory: 128-bit read-only loads
+    __device__ __forceinline__ void load_vec(const T* __restrict__ rec) {
+        constexpr int PER = 16 / (int)sizeof(T);
+        constexpr int NV = (N + PER - 1) / PER;
+        const int4* p = reinterpret_cast<const int4*>(rec);
+        T buf[NV * PER];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int4 w = __ldg(p + q);
+            if constexpr (sizeof(T) == 4) {
+                buf[4 * q] = __int_as_float(w.x); buf[4 * q + 1] = __int_as_float(w.y);
+                buf[4 * q + 2] = __int_as_float(w.z); buf[4 * q + 3] = __int_as_float(w.w);
+            } else {
+                buf[2 * q] = __hiloint2double(w.y, w.x); buf[2 * q + 1] = __hiloint2double(w.w, w.z);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = buf[k];
+    }
 };
 
 // rec holds one leaf record.  Arithmetic follows the reference's operation order (adapt.py:97-139
@@ -285,10 +314,11 @@ __device__ __forceinline__ T eval_record(const Record<BASIS, ORDER, T>& r, T x, 
     }
 }
 
-template <int BASIS, int ORDER, typename T, int STRIDE = 1>
+template <int BASIS, int ORDER, typename T, int STRIDE = 1, bool VEC = false>
 __device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order) {
     Record<BASIS, ORDER, T> r;
-    r.template load<STRIDE>(rec);
+    if constexpr (VEC) r.load_vec(rec);
+    else r.template load<STRIDE>(rec);
     return eval_record<BASIS, ORDER, T>(r, x, inv_order);
 }
 
@@ -334,14 +364,15 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
     Lookup<T> lk;
     lk.init(tv, base);
     constexpr int CP = Copies<T, MODE>::value;                     // copies per record element
-    constexpr int R = rec_stride(BASIS, ORDER) * CP;               // record stride in elements
+    constexpr int R = rec_stride_for<BASIS, ORDER, T, MODE>() * CP; // record stride in elements
+    constexpr bool VEC = (MODE == kGlobal);                        // 128-bit record loads
     // bank-private layout: lane l reads copy l (float) / l mod 16 (double) of every element
     const T* records = reinterpret_cast<const T*>(base + tv.off_records) + (threadIdx.x & (CP - 1));
     const T inv_order = (T)tv.inv_order;
 
     auto f = [&](T xv) -> T {
         const int i = lk.leaf(xv);
-        return eval_leaf<BASIS, ORDER, T, CP>(records + i * R, xv, inv_order);
+        return eval_leaf<BASIS, ORDER, T, CP, VEC>(records + i * R, xv, inv_order);
     };
 
     using V = typename Vec<T>::type;
@@ -411,12 +442,13 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 #endif
         if (uniform) {
             Record<BASIS, ORDER, T> rec;
-            rec.template load<CP>(records + li[0] * R);
+            if constexpr (VEC) rec.load_vec(records + li[0] * R);
+            else rec.template load<CP>(records + li[0] * R);
 #pragma unroll
             for (int e = 0; e < NE; ++e) xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
         } else {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T, CP>(records + li[e] * R, xs[e], inv_order);
+            for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T, CP, VEC>(records + li[e] * R, xs[e], inv_order);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -460,7 +492,7 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
     Lookup<T> lk;
     lk.init(tv, base);
     const T* records = reinterpret_cast<const T*>(base + tv.off_records);
-    constexpr int R = rec_stride(BASIS, ORDER);
+    constexpr int R = rec_stride_for<BASIS, ORDER, T, MODE>();
     const T inv_order = (T)tv.inv_order;
     double acc = 0.0;
     const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;

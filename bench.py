@@ -51,6 +51,26 @@ DEFAULT_WORKLOAD = "cfg2_j0_cheb_o6_f32"
 CPU_SAMPLE_LOG2 = 26
 
 
+NCU_SUMMARIES = {   # workload -> committed `ncu --set full` summary (tools/ncu_summary.py)
+    "cfg2_j0_cheb_o6_f32": "r1_ncu_cfg2_cheb_o6_f32.json",
+    "cfg3_j0_cheb_o13_f64": "r1_ncu_cfg3_cheb_o13_f64.json",
+}
+
+
+def ncu_traffic(workload, points_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the eval kernel, from the committed
+    ncu capture of the same workload and launch size (profiles/); None when there is none."""
+    name = NCU_SUMMARIES.get(workload)
+    path = os.path.join(ROOT, "profiles", name) if name else None
+    if not path or not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        d = json.load(fh)
+    if d.get("points_per_launch") != points_per_launch or not d.get("launches"):
+        return None
+    return d["launches"][0]["derived"]["dram_traffic_bytes"]
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -326,7 +346,8 @@ def main():
     algo_bytes = 2.0 * esz * n_local
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload, n_local),
+                "algorithmic_bytes_per_launch": algo_bytes,
                 "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs, burst copy)" % peak_kind,
                 "kernel": "ai::eval_kernel<%s,%d,%s>" % ({"chebyshev": "kCheb", "legendre": "kLeg", "monomial": "kMono"}[flat.basis],
                                                          flat.order, "float" if esz == 4 else "double"),

@@ -508,6 +508,30 @@ def dtype_np(t):
     return np.float32 if t == torch.float32 else np.float64
 
 
+def test_more_than_2_to_31_points():
+    """Element counts beyond int32 (byte offsets beyond 2^33): 64-bit indexing end to end."""
+    g = golden("approx__32o6-p1.19209289551e-06")
+    f = tables.flatten(g)
+    tab = dev_table(g.name)
+    n = (1 << 31) + 4099
+    x = _device_uniform(n, 0.0, 20.0, torch.float32, seed=99)
+    y = torch.full((n,), float("nan"), dtype=torch.float32, device="cuda")
+    tab.eval_ptr(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert not bool(torch.isnan(y[-8192:]).any()) and not bool(torch.isnan(y[:8192]).any())
+    assert int(torch.isnan(y).sum()) == 0                              # every element was written
+    for sl in (slice(0, 4096), slice((1 << 31) - 2048, (1 << 31) + 2048), slice(n - 4099, n)):
+        xs, ys = x[sl].cpu().numpy(), y[sl].cpu().numpy()
+        y_o = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, xs)
+        scale = oracle_np.error_scale(f.breaks, f.coef, f.basis, f.order, xs)
+        assert np.all(np.abs(ys.astype(np.float64) - y_o) <= value_tolerance(np.float32, scale, GPU_ULPS))
+    idx = torch.empty(1 << 16, dtype=torch.int32, device="cuda")
+    off = n - (1 << 16)
+    tab.index_ptr(x.data_ptr() + off * 4, idx.data_ptr(), 1 << 16, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), oracle_np.leaf_index(f.breaks, x[off:].cpu().numpy()))
+
+
 @pytest.mark.parametrize("name,log2n", [("approx__32o6-p1.19209289551e-06", 28),      # BASELINE config 2
                                         ("gen__cfg3_j0_cheb_o13_f64", 30),            # BASELINE config 3
                                         ("gen__cfg4_f1_leg_o7_f32", 28)])             # BASELINE config 4

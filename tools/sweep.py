@@ -74,8 +74,20 @@ def main():
     print("%-42s %-9s %3s %-4s %5s %2s %7s | %9s %8s %6s | %9s %8s %6s" % (
         "table", "basis", "n", "T", "L", "K", "smemB", "rand ms", "Gpt/s", "%hbm", "sort ms", "Gpt/s", "%hbm"))
     for name in names:
-        g = tables.load_golden(name)
-        f = tables.flatten(g)
+        if name.startswith("synth:"):
+            # synth:<leaves>:<order>:<f32|f64>  -- uniform leaves on [0,16], Chebyshev fit of sin(3x)
+            from numpy.polynomial import chebyshev as C
+            _, nl, order, tname = name.split(":")
+            nl, order, dt = int(nl), int(order), (np.float32 if tname == "f32" else np.float64)
+            br = np.linspace(0.0, 16.0, nl + 1).astype(dt)
+            nodes = np.cos(np.pi * (np.arange(order + 1) + 0.5) / (order + 1))
+            mids, half = (br[:-1].astype(np.float64) + br[1:]) / 2, (br[1:].astype(np.float64) - br[:-1]) / 2
+            vals = np.sin(3 * (mids[:, None] + half[:, None] * nodes[None, :]))
+            co = np.stack([C.chebfit(nodes, v, order) for v in vals]).astype(dt)
+            f = tables.FlatTable("chebyshev", order, dt, br, co)
+        else:
+            g = tables.load_golden(name)
+            f = tables.flatten(g)
         tab = tables.DeviceTable(f, 0)
         info = tab.info()
         tdt = torch.float32 if f.dtype == np.float32 else torch.float64
@@ -88,7 +100,8 @@ def main():
         y = torch.empty_like(x)
         row = {"table": name, "basis": f.basis, "order": f.order, "dtype": f.dtype.name, "leaves": f.n_leaves,
                "search_steps": info["search_steps"], "image_bytes": info["image_bytes"],
-               "blocks_per_sm": info["blocks_per_sm"], "grid_cells": info["grid_cells"]}
+               "blocks_per_sm": info["blocks_per_sm"], "grid_cells": info["grid_cells"],
+               "residency": info["residency"], "lookup_mode": info["lookup_mode"], "smem_bytes": info["smem_bytes"]}
         for order in ("random", "sorted"):
             if order == "sorted":
                 x = torch.sort(x)[0]
