@@ -35,7 +35,8 @@ class TableInfo(ctypes.Structure):
         ("device", ctypes.c_int32), ("n_leaves", ctypes.c_int64), ("grid_cells", ctypes.c_int32),
         ("grid_log2_scale", ctypes.c_int32), ("search_steps", ctypes.c_int32),
         ("record_stride", ctypes.c_int32), ("image_bytes", ctypes.c_int64),
-        ("smem_bytes", ctypes.c_int64), ("residency", ctypes.c_int32), ("smem_resident", ctypes.c_int32), ("lookup_mode", ctypes.c_int32), ("block_threads", ctypes.c_int32),
+        ("smem_bytes", ctypes.c_int64), ("residency", ctypes.c_int32), ("bank_copies", ctypes.c_int32),
+        ("smem_resident", ctypes.c_int32), ("lookup_mode", ctypes.c_int32), ("block_threads", ctypes.c_int32),
         ("blocks_per_sm", ctypes.c_int32), ("sm_count", ctypes.c_int32),
         ("lower_bound", ctypes.c_double), ("upper_bound", ctypes.c_double),
     ]

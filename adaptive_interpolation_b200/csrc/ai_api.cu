@@ -91,7 +91,8 @@ struct ai_table {
     int blocks_per_sm = 1, sm_count = 1;
     int smem_resident = 1;
     int rank_mode = 0;
-    int mode = ai::kSmem;              // table residency: kSmem / kSmemBank / kGlobal
+    int mode = ai::kSmem;              // table residency: kSmem / kSmemBank / kGlobal / kSmemBankN
+    int copies = 1;                    // bank modes: copies per element
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     HostPipe pipe;
@@ -264,6 +265,7 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     t->rstride = R;
     t->view.image_bytes = (int)total;
     t->view.n_records_elems = (int)(L * R);
+    t->view.n_breaks_elems = (int)(L + 1 + pad);
     t->view.off_first = off_first;
     t->view.off_breaks = off_breaks;
     t->view.off_records = off_records;
@@ -326,18 +328,39 @@ int finish_table(ai_table* t) {
 
     // ---- table residency -------------------------------------------------------------------
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
-    const int copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
-    const size_t bank_bytes = (size_t)t->view.off_records + (size_t)L * t->rstride * esz * copies;
+    const int full_copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
+    // shared-memory bytes of the bank layouts with `cp` copies: [grid table][breaks x cp][records x cp]
+    auto bank_layout = [&](int cp, int* soff_b, int* soff_r) -> size_t {
+        const size_t ob = (size_t)t->view.off_breaks;
+        const size_t orr = ob + (size_t)round_up16((size_t)t->view.n_breaks_elems * esz * cp);
+        if (soff_b) *soff_b = (int)ob;
+        if (soff_r) *soff_r = (int)orr;
+        return orr + (size_t)round_up16((size_t)t->view.n_records_elems * esz * cp);
+    };
     // leaves a warp can address without two of them sharing a bank (odd record stride)
-    const int64_t conflict_free_leaves = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
-    int mode = ai::kSmem;
-    if (go_global) mode = ai::kGlobal;
-    else if (L > conflict_free_leaves && bank_bytes <= smem_cap) mode = ai::kSmemBank;
-    if (!go_global && forced == ai::kSmem) mode = ai::kSmem;
-    if (!go_global && forced == ai::kSmemBank && bank_bytes <= smem_cap) mode = ai::kSmemBank;
+    const int64_t conflict_free_leaves = full_copies;
+    int mode = ai::kSmem, copies = 1;
+    if (go_global) {
+        mode = ai::kGlobal;
+    } else if (L > conflict_free_leaves || forced == ai::kSmemBank || forced == ai::kSmemBankN) {
+        if (bank_layout(full_copies, nullptr, nullptr) <= smem_cap && forced != ai::kSmemBankN) {
+            mode = ai::kSmemBank; copies = full_copies;
+        } else if (gp.K == 0 || forced == ai::kSmemBankN) {
+            // partial replication pays only when no search follows (measured: the 429-leaf 64o5
+            // table 39% -> 44% of HBM on random points; config 4's 220-leaf K=6 table gets slower)
+            for (int cp = full_copies / 2; cp >= 2; cp /= 2)
+                if (bank_layout(cp, nullptr, nullptr) <= smem_cap) { mode = ai::kSmemBankN; copies = cp; break; }
+        }
+    }
+    if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
     t->mode = mode;
+    t->copies = copies;
+    t->view.copies = copies;
     t->smem_resident = (mode != ai::kGlobal);
-    t->eval_smem = (mode == ai::kGlobal) ? 0 : (mode == ai::kSmemBank ? (int)bank_bytes : t->view.image_bytes);
+    t->eval_smem = 0;
+    if (mode == ai::kSmem) t->eval_smem = t->view.image_bytes;
+    if (mode == ai::kSmemBank || mode == ai::kSmemBankN)
+        t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
     t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
     AI_CUDA(cudaMalloc(&t->d_image, image.size()));
     AI_CUDA(cudaMemcpy(t->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
@@ -746,6 +769,7 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->image_bytes = t->view.image_bytes;
     info->smem_bytes = t->eval_smem;
     info->residency = t->mode;
+    info->bank_copies = t->copies;
     info->smem_resident = t->smem_resident;
     info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : 0);
     info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;

@@ -17,7 +17,7 @@ struct Unit {
         return cudaGetLastError();
     }
     static cudaError_t sum(const LaunchCfg& c, const TableView& tv, const T* x, double* r, long long n) {
-        if constexpr (MODE == kSmemBank) {
+        if constexpr (MODE == kSmemBank || MODE == kSmemBankN) {
             return cudaErrorInvalidValue;
         } else {
             eval_sum_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, r, n);
@@ -30,7 +30,7 @@ struct Unit {
             e = cudaFuncSetAttribute(eval_kernel<BASIS, ORDER, T, MODE>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
             if (e != cudaSuccess) return e;
-            if constexpr (MODE != kSmemBank) {
+            if constexpr (MODE == kSmem || MODE == kGlobal) {
                 e = cudaFuncSetAttribute(eval_sum_kernel<BASIS, ORDER, T, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
                 if (e != cudaSuccess) return e;
@@ -49,6 +49,7 @@ struct Switch {
             if (mode == kSmem) return Unit<BASIS, T, ORDER, kSmem>::eval(a...);
             if (mode == kSmemBank) return Unit<BASIS, T, ORDER, kSmemBank>::eval(a...);
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::eval(a...);
+            if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::eval(a...);
             return cudaErrorInvalidValue;
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::eval(order, mode, a...);
@@ -67,6 +68,7 @@ struct Switch {
             if (mode == kSmem) return Unit<BASIS, T, ORDER, kSmem>::prepare(smem_bytes, bps);
             if (mode == kSmemBank) return Unit<BASIS, T, ORDER, kSmemBank>::prepare(smem_bytes, bps);
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::prepare(smem_bytes, bps);
+            if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::prepare(smem_bytes, bps);
             return cudaErrorInvalidValue;
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::prepare(order, mode, smem_bytes, bps);

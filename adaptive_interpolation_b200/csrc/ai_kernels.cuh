@@ -58,7 +58,10 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              leaves than banks otherwise serialise 2-4x on random inputs)
 //   kGlobal    nothing staged: grid table, breakpoints and records are read through L1/L2 from
 //              the global image (tables too large for shared memory)
-enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2 };
+//   kSmemBankN as kSmemBank with a run-time power-of-two copy count < 32 (16): tables whose full
+//              replication does not fit in shared memory (lanes l mod N share a copy)
+// In both bank modes the breakpoint array read by the search is replicated the same way.
+enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3 };
 template <typename T, int MODE> struct Copies {
     static constexpr int value = (MODE == kSmemBank) ? (sizeof(T) == 4 ? 32 : 16) : 1;
 };
@@ -72,6 +75,9 @@ struct TableView {
     int off_records;               // T rec[L][R]           : [a, 2/(b-a), c0..cn, pad]
     int n_leaves;                  // L
     int n_records_elems;           // L * R (elements in the packed record array)
+    int n_breaks_elems;            // L + 1 + padding (elements in the breakpoint array)
+    int copies;                    // bank modes: copies per record / breakpoint element
+    int soff_breaks, soff_records; // bank modes: byte offsets of the replicated sections in shared memory
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
     int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit
@@ -129,6 +135,7 @@ template <typename T> struct Lookup {
     unsigned div_mul, div_shift, div_add, cont;
     const unsigned* first;         // packed 8- or 16-bit entries, read as 32-bit words
     const T* breaks;
+    int bstride;                   // 1, or the copy count when breaks[] is bank-replicated
 
     __device__ __forceinline__ void init(const TableView& tv, const unsigned char* base) {
         scale = (T)tv.scale; lo = (T)tv.lo; hi = (T)tv.hi;
@@ -137,6 +144,12 @@ template <typename T> struct Lookup {
         div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
         first = reinterpret_cast<const unsigned*>(base + tv.off_first);
         breaks = reinterpret_cast<const T*>(base + tv.off_breaks);
+        bstride = 1;
+    }
+    // bank modes: breaks[] lives at soff_breaks, `copies` copies per element, lane l reads copy l
+    __device__ __forceinline__ void use_replicated_breaks(const TableView& tv, const unsigned char* base) {
+        breaks = reinterpret_cast<const T*>(base + tv.soff_breaks) + (threadIdx.x & (tv.copies - 1));
+        bstride = tv.copies;
     }
     // fine cell of x relative to the first cell, clamped to [0, G)
     __device__ __forceinline__ int cell(T x) const {
@@ -170,7 +183,7 @@ template <typename T> struct Lookup {
     // one step of the branch-free forward binary search (step s = 2^k); breaks[] is +inf padded
     __device__ __forceinline__ int refine(T x, int i, int s) const {
         const int j = i + s;
-        return !(x < breaks[j]) ? j : i;
+        return !(x < breaks[j * bstride]) ? j : i;
     }
 
     // leaf ordinals of N points held in registers.  Mode branches are warp-uniform and sit
@@ -219,6 +232,10 @@ template <int BASIS, int ORDER, typename T> struct Record {
     __device__ __forceinline__ void load(const T* __restrict__ rec) {
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = rec[k * STRIDE];
+    }
+    __device__ __forceinline__ void load_strided(const T* __restrict__ rec, int stride) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = rec[k * stride];
     }
     // 16-byte aligned record in global memory: 128-bit read-only loads
     __device__ __forceinline__ void load_vec(const T* __restrict__ rec) {
@@ -333,18 +350,25 @@ template <typename T, int MODE>
 __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
     if constexpr (MODE == kGlobal) {
         return tv.image;
-    } else {
+    } else if constexpr (MODE == kSmem) {
         const int4* src = reinterpret_cast<const int4*>(tv.image);
         int4* dst = reinterpret_cast<int4*>(smem);
-        const int head = (MODE == kSmemBank) ? tv.off_records : tv.image_bytes;
-        for (int k = threadIdx.x; k < head / 16; k += blockDim.x) dst[k] = __ldg(src + k);
-        if constexpr (MODE == kSmemBank) {
-            constexpr int CP = Copies<T, MODE>::value;
-            const T* rsrc = reinterpret_cast<const T*>(tv.image + tv.off_records);
-            T* rdst = reinterpret_cast<T*>(smem + tv.off_records);
-            const int n = tv.n_records_elems * CP;
-            for (int k = threadIdx.x; k < n; k += blockDim.x) rdst[k] = __ldg(rsrc + k / CP);
-        }
+        for (int k = threadIdx.x; k < tv.image_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+        __syncthreads();
+        return smem;
+    } else {
+        // grid table as is; breakpoints and records written `copies` times, element-interleaved
+        const int4* src = reinterpret_cast<const int4*>(tv.image);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int k = threadIdx.x; k < tv.off_breaks / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+        const int cp = (MODE == kSmemBank) ? Copies<T, MODE>::value : tv.copies;
+        const int sh = 31 - __clz(cp);
+        const T* bsrc = reinterpret_cast<const T*>(tv.image + tv.off_breaks);
+        T* bdst = reinterpret_cast<T*>(smem + tv.soff_breaks);
+        for (int k = threadIdx.x; k < tv.n_breaks_elems * cp; k += blockDim.x) bdst[k] = __ldg(bsrc + (k >> sh));
+        const T* rsrc = reinterpret_cast<const T*>(tv.image + tv.off_records);
+        T* rdst = reinterpret_cast<T*>(smem + tv.soff_records);
+        for (int k = threadIdx.x; k < tv.n_records_elems * cp; k += blockDim.x) rdst[k] = __ldg(rsrc + (k >> sh));
         __syncthreads();
         return smem;
     }
@@ -363,16 +387,28 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 
     Lookup<T> lk;
     lk.init(tv, base);
-    constexpr int CP = Copies<T, MODE>::value;                     // copies per record element
-    constexpr int R = rec_stride_for<BASIS, ORDER, T, MODE>() * CP; // record stride in elements
+    constexpr bool kBank = (MODE == kSmemBank || MODE == kSmemBankN);
     constexpr bool VEC = (MODE == kGlobal);                        // 128-bit record loads
-    // bank-private layout: lane l reads copy l (float) / l mod 16 (double) of every element
-    const T* records = reinterpret_cast<const T*>(base + tv.off_records) + (threadIdx.x & (CP - 1));
+    // copies per record element: compile-time except in kSmemBankN
+    const int cp = (MODE == kSmemBank) ? Copies<T, MODE>::value : (MODE == kSmemBankN ? tv.copies : 1);
+    const int R = rec_stride_for<BASIS, ORDER, T, MODE>() * cp;    // record stride in elements
+    // bank-private layout: lane l reads copy l mod cp of every element
+    const T* records = reinterpret_cast<const T*>(base + (kBank ? tv.soff_records : tv.off_records))
+                       + (threadIdx.x & (cp - 1));
+    if constexpr (kBank) lk.use_replicated_breaks(tv, base);
     const T inv_order = (T)tv.inv_order;
 
+    auto load_record = [&](Record<BASIS, ORDER, T>& r, int leaf) {
+        const T* p = records + leaf * R;
+        if constexpr (VEC) r.load_vec(p);
+        else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);
+        else if constexpr (MODE == kSmemBankN) r.load_strided(p, cp);
+        else r.template load<1>(p);
+    };
     auto f = [&](T xv) -> T {
-        const int i = lk.leaf(xv);
-        return eval_leaf<BASIS, ORDER, T, CP, VEC>(records + i * R, xv, inv_order);
+        Record<BASIS, ORDER, T> r;
+        load_record(r, lk.leaf(xv));
+        return eval_record<BASIS, ORDER, T>(r, xv, inv_order);
     };
 
     using V = typename Vec<T>::type;
@@ -442,13 +478,16 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 #endif
         if (uniform) {
             Record<BASIS, ORDER, T> rec;
-            if constexpr (VEC) rec.load_vec(records + li[0] * R);
-            else rec.template load<CP>(records + li[0] * R);
+            load_record(rec, li[0]);
 #pragma unroll
             for (int e = 0; e < NE; ++e) xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
         } else {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) xs[e] = eval_leaf<BASIS, ORDER, T, CP, VEC>(records + li[e] * R, xs[e], inv_order);
+            for (int e = 0; e < NE; ++e) {
+                Record<BASIS, ORDER, T> rec;
+                load_record(rec, li[e]);
+                xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+            }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -486,7 +525,7 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
-    static_assert(MODE != kSmemBank, "the reduction variant uses the packed layouts only");
+    static_assert(MODE == kSmem || MODE == kGlobal, "the reduction variant uses the packed layouts only");
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned char* base = table_base<T, MODE>(tv, smem);
     Lookup<T> lk;
@@ -520,7 +559,7 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 index_kernel(const TableView tv, const T* __restrict__ x, int32_t* __restrict__ idx, long long n) {
-    static_assert(MODE != kSmemBank, "lookup only: records are not read");
+    static_assert(MODE == kSmem || MODE == kGlobal, "lookup only: records are not read");
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned char* base = table_base<T, MODE>(tv, smem);
     Lookup<T> lk;

@@ -162,10 +162,10 @@ def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
-    """Packed shared memory / bank-private shared memory / global (L2-resident): same leaf,
-    same arithmetic, so identical indices and identical value bits on every table."""
+    """Packed shared memory / bank-private shared memory (full or partial replication) / global
+    (L2-resident): same leaf, same arithmetic, so identical indices and value bits on every table."""
     g = golden(name)
     want_y = gpu_eval(dev_table(name), g.x)
     monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
@@ -291,6 +291,9 @@ def test_residency_selection():
     assert res["approx__32o3-p1.19209289551e-06"]["residency"] == 1           # 62 leaves, fp32
     assert res["approx__64o7-p2.22044604925e-14"]["residency"] == 1           # 64 leaves, fp64
     assert res["approx__64o6-p1.19209289551e-06"]["residency"] == 0           # 15 leaves, fp64
+    assert res["approximations__64o5-p2.22044604925e-14"]["residency"] == 3   # 429 leaves: partial copies
+    assert res["approximations__64o5-p2.22044604925e-14"]["bank_copies"] in (2, 4, 8)
+    assert res["gen__cfg4_f1_leg_o7_f64"]["residency"] == 0                   # too big for 16 copies, has a search
     for name, info in res.items():
         assert info["smem_bytes"] <= 227 * 1024
 
@@ -309,7 +312,7 @@ def test_saved_tables_need_no_search():
     for name in SAVED:
         info = dev_table(name).info()
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1)
+        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1, 3)
     for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
         assert dev_table(name).info()["search_steps"] >= 1
 
