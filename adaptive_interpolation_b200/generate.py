@@ -112,11 +112,14 @@ def device_table(approx, device=None):
     stamp = _stamp(approx)
     if ent is None or ent.ref() is not approx or ent.stamp != stamp:
         ent = _Entry()
-        ent.ref = weakref.ref(approx)
         ent.tables = {}
         ent.stamp = stamp
+        try:
+            ent.ref = weakref.ref(approx)
+            weakref.finalize(approx, _REGISTRY.pop, key, None)
+        except TypeError:                  # object without weakref support: keep it alive instead
+            ent.ref = (lambda obj=approx: obj)
         _REGISTRY[key] = ent
-        weakref.finalize(approx, _REGISTRY.pop, key, None)
     if device not in ent.tables:
         ent.tables[device] = tables.DeviceTable(tables.flatten(approx), device)
     return ent.tables[device]
