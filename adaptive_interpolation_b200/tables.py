@@ -88,6 +88,64 @@ def flatten_tree_1d(tree_1d, order):
     return a, b, np.array(coef, dtype=t.dtype).reshape(len(a), n + 1)
 
 
+def flatten_nodes(root, basis, order, dtype):
+    """Flatten the fitter's raw tree (adapt.py:14-48 Tree/Node objects, node.data = [mid, coeff,
+    [a, b], err], adapt.py:233 / :381) straight to a FlatTable.  This is the route for deep or
+    skewed trees that the reference's Approximator constructor cannot take (approximator.py:98,
+    158, 178 -- SURVEY.md appendix C-2/C-3).  Children whose `data` was never set (the fitter
+    returned early with accurate=False, adapt.py:206-227) make their parent the leaf, as the
+    reference's own evaluate_tree effectively does (approximator.py:252-256)."""
+    dt = np.dtype(dtype)
+    a, b, coef = [], [], []
+    stack = [root]
+    while stack:
+        node = stack.pop()
+        left, right = getattr(node, "left", 0), getattr(node, "right", 0)
+        is_leaf = (left == 0 or right == 0 or left is node or right is node
+                   or not isinstance(getattr(left, "data", 0), (list, tuple))
+                   or not isinstance(getattr(right, "data", 0), (list, tuple)))
+        if is_leaf:
+            data = node.data
+            a.append(data[2][0])
+            b.append(data[2][1])
+            c = np.asarray(data[1], dtype=np.float64)
+            if len(c) != int(order) + 1:
+                raise ValueError("leaf has %d coefficients, expected order+1 = %d" % (len(c), int(order) + 1))
+            coef.append(c)
+        else:
+            stack.append(right)
+            stack.append(left)
+    a = np.asarray(a, dtype=dt)
+    b = np.asarray(b, dtype=dt)
+    if np.any(a[1:] != b[:-1]):
+        k = int(np.nonzero(a[1:] != b[:-1])[0][0])
+        raise ValueError("leaves %d and %d are not contiguous (%r != %r)" % (k, k + 1, b[k], a[k + 1]))
+    return FlatTable(basis, order, dt, np.concatenate([a, b[-1:]]), np.asarray(coef))
+
+
+def decode_packed_map(approx):
+    """Decode the reference's packed uniform-grid map into (leaf, first_cell, n_cells) per cell.
+
+    Two encodings exist in the saved tables:
+      V2/V3 `cmap`: leaf | l << D | L << 2D with D = max_level + 1   (approximator.py:155-188)
+      V1 `ci*` files: `map` itself is int64 leaf | l << 20 | r << 40  (run_perf.py:315-319),
+                      r = l + L
+    Used to check that tables fitted for the "calc intervals" variant (generate.py:335-348)
+    describe exactly the leaves this library flattens; the kernels do not read it."""
+    cmap = np.asarray(getattr(approx, "cmap", []))
+    if cmap.size:
+        D = int(approx.num_levels)              # tree.max_level + 1
+        mask = (1 << D) - 1
+        c = cmap.astype(np.int64)
+        return c & mask, (c >> D) & mask, c >> (2 * D)
+    m = np.asarray(approx.map).astype(np.int64)
+    if m.size and m.max() >= (1 << 20):
+        mask = (1 << 20) - 1
+        leaf, l, r = m & mask, (m >> 20) & mask, m >> 40
+        return leaf, l, r - l
+    raise ValueError("this table carries no packed map")
+
+
 def table_dtype(approx):
     dt = getattr(approx, "dtype", None)
     if dt is None:

@@ -488,6 +488,23 @@ def test_integration_stub_pure_ctypes():
     assert lib.ai_table_destroy(h) == 0
 
 
+def test_exact_interpolants_like_the_reference_test():
+    """tests/performance_tests.py:112-128: monomial fits of polynomials are exact; the reference
+    asserts ||est - f||_inf / ||f||_inf < 1e-15 on linspace(-10, 10, 100) with its Python evaluator.
+    Same points, same functions, GPU evaluation; 4e-15 allows for the fused Horner rounding."""
+    x = np.linspace(-10, 10, 100, dtype=np.float64)
+    funcs = {"gen__line1_mono_o1_f64": lambda t: 3 * t + 7,
+             "gen__poly4_mono_o4_f64": lambda t: 4.123 * t**4 - 5.6 * t**3 - t**2 + 4.5,
+             "gen__poly6_mono_o6_f64": lambda t: t**6 - 3 * t**5 - 2 * t**4 + t - 3}
+    for name, fn in funcs.items():
+        y = gpu_eval(dev_table(name), x)
+        rel = np.max(np.abs(y - fn(x))) / np.max(np.abs(fn(x)))
+        y_ref = oracle_np.evaluate(*(lambda f: (f.breaks, f.coef, f.basis, f.order))(tables.flatten(golden(name))), x)
+        rel_ref = np.max(np.abs(y_ref - fn(x))) / np.max(np.abs(fn(x)))
+        report(test="exact_interpolants", table=name, rel=rel, rel_ref=rel_ref)
+        assert rel < max(4e-15, 2 * rel_ref), (name, rel, rel_ref)
+
+
 def test_reference_parity_test_intent():
     """tests/generate_tests.py:27: ||app.evaluate(x) - run_code(x)||_inf / max|f| < 1e-12 (fp64)."""
     for name in ("gen__cossin_cheb_o10_f64", "gen__sinsin_leg_o10_f64", "gen__cfg1_sinsin_cheb_o3_f64"):

@@ -68,6 +68,47 @@ def test_single_leaf_and_order_one():
     assert f.n_leaves == 1 and f.order == 1 and f.coef.shape == (1, 2)
 
 
+def test_flatten_raw_node_tree_with_pruning():
+    """adapt.py Tree/Node objects -> FlatTable, including a dataless pair of children
+    (accurate=False early return, adapt.py:206-227): their parent becomes the leaf."""
+    def node(a, b, c, children=None):
+        n = app.Node()
+        n.data = [(a + b) / 2.0, list(c), [a, b], 0.0]
+        if children:
+            n.left, n.right = children
+        return n
+    dead_l, dead_r = app.Node(), app.Node()                  # data == 0
+    leaf0 = node(0.0, 1.0, [1, 2, 3])
+    leaf1 = node(1.0, 1.5, [4, 5, 6], (dead_l, dead_r))      # children never fitted
+    leaf2 = node(1.5, 2.0, [7, 8, 9])
+    root = node(0.0, 2.0, [0, 0, 0], (leaf0, node(1.0, 2.0, [0, 0, 0], (leaf1, leaf2))))
+    f = tables.flatten_nodes(root, "legendre", 2, np.float32)
+    assert np.array_equal(f.breaks, np.array([0, 1, 1.5, 2], dtype=np.float32))
+    assert np.array_equal(f.coef, np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.float32))
+    with pytest.raises(ValueError):
+        tables.flatten_nodes(node(0.0, 1.0, [1, 2]), "legendre", 2, np.float32)      # wrong order
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if n.startswith("approx")])
+def test_packed_map_describes_the_flattened_leaves(name):
+    """The reference's packed grid maps ("calc intervals", approximator.py:155-188 and the int64
+    `map` of the ci* files) decode to exactly the leaves we flatten from tree_1d."""
+    g = golden(name)
+    try:
+        leaf, l, n_cells = tables.decode_packed_map(g)
+    except ValueError:
+        pytest.skip("no packed map in this schema version")
+    f = tables.flatten(g)
+    cells = len(leaf)
+    w = (float(g.upper_bound) - float(g.lower_bound)) / cells
+    assert leaf.min() == 0 and leaf.max() == f.n_leaves - 1
+    for c in range(cells):
+        i = int(leaf[c])
+        assert l[c] <= c < l[c] + n_cells[c]
+        assert abs(float(f.breaks[i]) - (float(g.lower_bound) + l[c] * w)) <= 1e-12 * max(1.0, abs(float(f.breaks[i])))
+        assert abs(float(f.breaks[i + 1]) - (float(g.lower_bound) + (l[c] + n_cells[c]) * w)) <= 1e-12 * max(1.0, abs(float(f.breaks[i + 1])))
+
+
 def _fake_reference_modules():
     """Modules named like the reference's so a pickle in the reference's schema can be produced
     without the reference (class identity in a pickle is just module + qualname)."""
@@ -150,6 +191,9 @@ def test_load_every_saved_pickle():
             g = tables.flatten(golden("%s__%s" % (d, fn)))
             assert np.array_equal(f.breaks, g.breaks) and np.array_equal(f.coef, g.coef)
             assert f.basis == g.basis and f.order == g.order and f.dtype == g.dtype
+            # the pickled fitter tree (adapt.py Node objects) flattens to the same table
+            fn_ = tables.flatten_nodes(ap.tree.root, ap.basis, ap.max_order, f.dtype)
+            assert np.array_equal(fn_.breaks, f.breaks) and np.array_equal(fn_.coef, f.coef)
             count += 1
     assert count == 27
 
