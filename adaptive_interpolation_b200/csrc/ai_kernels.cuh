@@ -133,36 +133,37 @@ template <typename T> struct Lookup {
     int g0, ghi, kstep, lmax;
     int fshift, rank_mode;
     unsigned div_mul, div_shift, div_add, cont;
-    const unsigned* first;         // packed 8- or 16-bit entries, read as 32-bit words
-    const T* breaks;
-    int bstride;                   // 1, or the copy count when breaks[] is bank-replicated
+    const unsigned char* first;    // packed 8-bit (L <= 256) or 16-bit entries
+    const unsigned char* bbase;    // breaks[] base (uniform); element j of this lane lives at
+    int bunit_log2;                //   bbase + (j << bunit_log2) + blane
+    int blane;                     // bank modes: byte offset of this lane's copy (< 1 << bunit_log2)
 
     __device__ __forceinline__ void init(const TableView& tv, const unsigned char* base) {
         scale = (T)tv.scale; lo = (T)tv.lo; hi = (T)tv.hi;
         g0 = tv.g0; ghi = (int)tv.hi; kstep = tv.kstep; lmax = tv.n_leaves - 1;
         fshift = tv.first_shift; rank_mode = tv.rank_mode;
         div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
-        first = reinterpret_cast<const unsigned*>(base + tv.off_first);
-        breaks = reinterpret_cast<const T*>(base + tv.off_breaks);
-        bstride = 1;
+        first = base + tv.off_first;
+        bbase = base + tv.off_breaks;
+        bunit_log2 = (sizeof(T) == 4) ? 2 : 3;
+        blane = 0;
     }
     // bank modes: breaks[] lives at soff_breaks, `copies` copies per element, lane l reads copy l
     __device__ __forceinline__ void use_replicated_breaks(const TableView& tv, const unsigned char* base) {
-        breaks = reinterpret_cast<const T*>(base + tv.soff_breaks) + (threadIdx.x & (tv.copies - 1));
-        bstride = tv.copies;
+        bbase = base + tv.soff_breaks;
+        bunit_log2 = ((sizeof(T) == 4) ? 2 : 3) + (31 - __clz(tv.copies));
+        blane = (int)(threadIdx.x & (tv.copies - 1)) * (int)sizeof(T);
     }
     // fine cell of x relative to the first cell, clamped to [0, G)
     __device__ __forceinline__ int cell(T x) const {
         if constexpr (sizeof(T) == 4) return cell_of(x, scale, lo, hi, g0);
         else return cell_of(x, scale, g0, ghi);
     }
-    // leaf holding the left edge of fine cell g, from the packed table in shared memory.
-    // Entries are bytes when L <= 256 (4 per 32-bit word: 80 cells = 20 words, conflict-free).
+    // leaf holding the left edge of fine cell g, from the packed table.  Entries are bytes when
+    // L <= 256 (80 cells = 20 words: conflict-free), else 16-bit.
+    template <typename E>
     __device__ __forceinline__ int table_guess(int g) const {
-        const unsigned w = first[g >> fshift];
-        const int sub = g & ((1 << fshift) - 1);
-        const int bits = 32 >> fshift;                       // 8 or 16
-        return (int)((w >> (sub * bits)) & ((1u << bits) - 1u));
+        return (int)reinterpret_cast<const E*>(first)[g];
     }
     // absolute fine cell of x, clamped to [g0, g0+G).  cvt.rmi.s32 saturates (NaN -> 0), so the
     // clamp can be done after the conversion in the integer domain (one 3-input min/max).
@@ -180,12 +181,6 @@ template <typename T> struct Lookup {
         const unsigned above = 0xfffffffeu << c;                 // bits strictly above c
         return (int)c - __popc(cont & ~above);
     }
-    // one step of the branch-free forward binary search (step s = 2^k); breaks[] is +inf padded
-    __device__ __forceinline__ int refine(T x, int i, int s) const {
-        const int j = i + s;
-        return !(x < breaks[j * bstride]) ? j : i;
-    }
-
     // leaf ordinals of N points held in registers.  Mode branches are warp-uniform and sit
     // OUTSIDE the per-point loops, so the N dependent chains interleave (ILP).
     template <int N>
@@ -195,15 +190,30 @@ template <typename T> struct Lookup {
             for (int e = 0; e < N; ++e) i[e] = rank_guess(x[e]);
             return;
         }
+        if (fshift == 2) {
 #pragma unroll
-        for (int e = 0; e < N; ++e) i[e] = table_guess(cell(x[e]));
-        if (kstep) {                      // tables whose breakpoints are off the grid
-            for (int s = kstep; s; s >>= 1) {
+            for (int e = 0; e < N; ++e) i[e] = table_guess<unsigned char>(cell(x[e]));
+        } else {
 #pragma unroll
-                for (int e = 0; e < N; ++e) i[e] = refine(x[e], i[e], s);
+            for (int e = 0; e < N; ++e) i[e] = table_guess<unsigned short>(cell(x[e]));
+        }
+        if (kstep) {
+            // Tables whose breakpoints are off the grid: branch-free forward binary search over
+            // the stored breakpoints (+inf padded past L).  The candidate is carried as a BYTE
+            // offset into breaks[] so that a step is add / load / compare / select.
+            const int unit = 1 << bunit_log2;
+#pragma unroll
+            for (int e = 0; e < N; ++e) i[e] = (i[e] << bunit_log2) + blane;
+            for (int sb = kstep << bunit_log2; sb >= unit; sb >>= 1) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) {
+                    const int q = i[e] + sb;
+                    const T b = *reinterpret_cast<const T*>(bbase + q);
+                    i[e] = !(x[e] < b) ? q : i[e];
+                }
             }
 #pragma unroll
-            for (int e = 0; e < N; ++e) i[e] = min(i[e], lmax);
+            for (int e = 0; e < N; ++e) i[e] = min(i[e] >> bunit_log2, lmax);   // drops blane (< unit)
         }
     }
     __device__ __forceinline__ int leaf(T x) const {
