@@ -36,6 +36,12 @@ namespace ai {
 #ifndef AI_LEG_CLENSHAW
 #define AI_LEG_CLENSHAW 1          // Legendre-like basis: Clenshaw (3 instr/degree) vs forward (5)
 #endif
+// Debug build (tools/tune.py "debug_bounds"): every table access is range-checked and traps.
+#ifdef AI_DEBUG_BOUNDS
+#define AI_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define AI_CHECK(cond) do { } while (0)
+#endif
 #ifndef AI_BLOCK
 #define AI_BLOCK 512               // threads per CTA
 #endif
@@ -131,6 +137,7 @@ __device__ __forceinline__ int cell_of(double x, double scale, int glo, int ghi)
 template <typename T> struct Lookup {
     T scale, lo, hi;
     int g0, ghi, kstep, lmax;
+    int nbreaks;                   // elements in breaks[] incl. +inf padding (bounds checks)
     int fshift, rank_mode;
     unsigned div_mul, div_shift, div_add, cont;
     const unsigned char* first;    // packed 8-bit (L <= 256) or 16-bit entries
@@ -141,7 +148,7 @@ template <typename T> struct Lookup {
     __device__ __forceinline__ void init(const TableView& tv, const unsigned char* base) {
         scale = (T)tv.scale; lo = (T)tv.lo; hi = (T)tv.hi;
         g0 = tv.g0; ghi = (int)tv.hi; kstep = tv.kstep; lmax = tv.n_leaves - 1;
-        fshift = tv.first_shift; rank_mode = tv.rank_mode;
+        fshift = tv.first_shift; rank_mode = tv.rank_mode; nbreaks = tv.n_breaks_elems;
         div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
         first = base + tv.off_first;
         bbase = base + tv.off_breaks;
@@ -163,7 +170,10 @@ template <typename T> struct Lookup {
     // L <= 256 (80 cells = 20 words: conflict-free), else 16-bit.
     template <typename E>
     __device__ __forceinline__ int table_guess(int g) const {
-        return (int)reinterpret_cast<const E*>(first)[g];
+        AI_CHECK(g >= 0 && g <= ghi - g0);
+        const int i = (int)reinterpret_cast<const E*>(first)[g];
+        AI_CHECK(i >= 0 && i <= lmax);
+        return i;
     }
     // absolute fine cell of x, clamped to [g0, g0+G).  cvt.rmi.s32 saturates (NaN -> 0), so the
     // clamp can be done after the conversion in the integer domain (one 3-input min/max).
@@ -178,8 +188,11 @@ template <typename T> struct Lookup {
     // the host for every fine cell); the leaf is the number of leaf starts at or before it.
     __device__ __forceinline__ int rank_guess(T x) const {
         const unsigned c = (cell_abs(x) * div_mul + div_add) >> div_shift;
+        AI_CHECK(c < 32u);
         const unsigned above = 0xfffffffeu << c;                 // bits strictly above c
-        return (int)c - __popc(cont & ~above);
+        const int i = (int)c - __popc(cont & ~above);
+        AI_CHECK(i >= 0 && i <= lmax);
+        return i;
     }
     // leaf ordinals of N points held in registers.  Mode branches are warp-uniform and sit
     // OUTSIDE the per-point loops, so the N dependent chains interleave (ILP).
@@ -208,6 +221,7 @@ template <typename T> struct Lookup {
 #pragma unroll
                 for (int e = 0; e < N; ++e) {
                     const int q = i[e] + sb;
+                    AI_CHECK(q >= 0 && (q >> bunit_log2) < nbreaks);
                     const T b = *reinterpret_cast<const T*>(bbase + q);
                     i[e] = !(x[e] < b) ? q : i[e];
                 }
@@ -409,6 +423,7 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
     const T inv_order = (T)tv.inv_order;
 
     auto load_record = [&](Record<BASIS, ORDER, T>& r, int leaf) {
+        AI_CHECK(leaf >= 0 && leaf < tv.n_leaves);
         const T* p = records + leaf * R;
         if constexpr (VEC) r.load_vec(p);
         else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Small driver for compute-sanitizer: every residency mode x lookup mode on a few tables,
+special inputs included, plus index / sum / host entry points.  Run as
+    compute-sanitizer --tool memcheck python tools/sanitize_case.py
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+TABLES = ["approx__32o6-p1.19209289551e-06", "approx__32o3-p1.19209289551e-06", "gen__cfg4_f1_leg_o7_f32",
+          "gen__cfg4_f1_leg_o7_f64", "approximations__64o5-p2.22044604925e-14", "gen__j0_mono_o13_f64",
+          "gen__cfg3_j0_cheb_o13_f64", "gen__line1_mono_o1_f64"]
+
+
+def child():
+    import numpy as np
+    import torch
+    from adaptive_interpolation_b200 import tables
+    for name in TABLES:
+        g = tables.load_golden(name)
+        tab = tables.DeviceTable(tables.flatten(g), 0)
+        info = tab.info()
+        x = np.concatenate([g.x, np.sort(g.x[np.isfinite(g.x)])[:3000]])
+        for n in (0, 1, 7, 4099, len(x)):
+            xd = torch.from_numpy(np.ascontiguousarray(x[:n])).cuda()
+            yd = torch.empty_like(xd)
+            idx = torch.empty(n, dtype=torch.int32, device="cuda")
+            res = torch.zeros(1, dtype=torch.float64, device="cuda")
+            tab.eval_ptr(xd.data_ptr(), yd.data_ptr(), n, None)
+            tab.index_ptr(xd.data_ptr(), idx.data_ptr(), n, None)
+            tab.sum_ptr(xd.data_ptr(), res.data_ptr(), n, None)
+            torch.cuda.synchronize()
+        tab.eval_host(x)
+        print(name, "mode", os.environ.get("AI_B200_FORCE_MODE", "auto"), "residency", info["residency"],
+              "lookup", info["lookup_mode"], "ok", flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "child":
+        child()
+    else:
+        for mode in (None, "0", "1", "2", "3"):
+            env = dict(os.environ)
+            if mode is not None:
+                env["AI_B200_FORCE_MODE"] = mode
+            r = subprocess.run([sys.executable, __file__, "child"], env=env)
+            if r.returncode != 0:
+                sys.exit(r.returncode)

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
+    "debug_bounds": ["AI_DEBUG_BOUNDS=1"],
     # tag: defines   (defaults: AI_BLOCK=512 AI_UNROLL=4 AI_PREFETCH=1 AI_UNIFORM_PATH=2 AI_MIN_BLOCKS=1)
     "t512_u6": ["AI_UNROLL=6", "AI_UNROLL_F64=6"],
     "t768_u6": ["AI_BLOCK=768", "AI_UNROLL=6", "AI_UNROLL_F64=6"],
