@@ -1,16 +1,18 @@
-"""Mirror of the reference facade adaptive_interpolation/adaptive_interpolation.py.
+"""Drop-in facade with the reference's public entry points, served by the CUDA backend.
 
-    make_interpolant(a, b, func, order, error, basis, adapt_type, dtype, accurate, optimizations)   :14
-    generate_code(approx, size=None, vector_width=1, cpu=False)                                     :37
-    write_to_file(file_path, approx) / load_from_file(file_path)                                    :78 / :91
-    run_approximation(x, approx) -> (run_time, output)                                              :111
-    run_code(x, approx, vectorized=None)      legacy spelling used by tests/generate_tests.py:26
+Entry points and where the reference defines them (adaptive_interpolation/adaptive_interpolation.py):
 
-Signatures, side effects (approx.vector_width / .size / .code) and error behaviour (bare
-Exception with the reference's messages) are kept; generate_code / run_approximation are
-re-pointed at the CUDA backend (generate.py in this package).  Fitting (make_interpolant) is the
-reference's CPU code, unchanged and out of scope: it is delegated to the reference package when
-that is importable.
+    make_interpolant(a, b, func, order, error, basis, adapt_type, dtype, accurate, optimizations)  :14
+    generate_code(approx, size=None, vector_width=1, cpu=False) -> str                             :37
+    write_to_file(file_path, approx) / load_from_file(file_path)                                   :78 / :91
+    run_approximation(x, approx) -> (run_time, output)                                             :111
+    run_code(x, approx, vectorized=None)   legacy spelling, tests/generate_tests.py:26
+
+Contract kept: signatures, the attributes set on the Approximator (vector_width, size, code), the
+bare `Exception` error convention and its message texts.  What differs is what happens underneath:
+"code" names a precompiled sm_100a kernel instead of holding generated source, and evaluation runs
+through libai_b200.so (see generate.py in this package).  The adaptive fit itself is the
+reference's CPU code and stays there; make_interpolant only forwards to it.
 """
 from __future__ import absolute_import
 
@@ -19,114 +21,128 @@ import pickle
 
 import numpy as np
 
-from . import approximator as app
+from . import approximator as _approximator
 from . import generate
+
+# --- message texts callers (and the reference's own tests) match on -------------------------------
+_MSG_CPU_NEEDS_SIZE = "The size must be known to generate cpu code."
+_MSG_ISPC_CHEB_ONLY = "ISPC generation only compatible with chebyshev interpolants currently."
+_MSG_WIDTH_AND_SIZE = ("Both vector width and domain_size must be given "
+                       "if running single-threaded code.")
+_MSG_BAD_BASIS = "Incorrect basis provided: monomial, chebyshev, legendre."
+_MSG_BAD_DTYPE = "Incorrect data type specified"
+_MSG_NO_CODE = ("Approximator class does not have any associated "
+                "code. Run a generate method to add code to the class.")
+_MSG_LOAD_FAILED = "Error loading instance from {0}"
+
+# basis name -> generator of the device "code" (reference: generate.gen_mono / gen_cheb / gen_leg)
+_DEVICE_GENERATORS = {
+    "monomial": generate.gen_mono,
+    "chebyshev": generate.gen_cheb,
+    "legendre": generate.gen_leg,
+}
+# upper bit width -> C type name stored in Approximator.dtype_name (reference :25-33)
+_DTYPE_NAMES = ((32, "float"), (64, "double"), (80, "long double"))
+
+
+def _dtype_name(dtype):
+    bits = int(dtype)
+    for limit, name in _DTYPE_NAMES:
+        if bits <= limit:
+            return name
+    raise Exception(_MSG_BAD_DTYPE)
 
 
 @contextlib.contextmanager
-def _numpy_compat():
-    """adapt.py:182-188 passes float sample counts to np.linspace, a TypeError on numpy >= 1.18
-    (SURVEY.md appendix C-1).  Cast them for the duration of a fit; the reference is untouched."""
-    real = np.linspace
+def _integer_linspace_counts():
+    """The reference fitter hands float sample counts to np.linspace (adapt.py:182-188), which
+    numpy >= 1.18 rejects.  While a fit runs, counts are truncated to int; nothing in the
+    reference is modified."""
+    original = np.linspace
 
     def linspace(start, stop, num=50, *args, **kwargs):
-        return real(start, stop, int(num), *args, **kwargs)
+        return original(start, stop, int(num), *args, **kwargs)
+
     np.linspace = linspace
     try:
         yield
     finally:
-        np.linspace = real
+        np.linspace = original
 
 
 def make_interpolant(a, b, func, order, error, basis="chebyshev",
                      adapt_type="Remez", dtype='64', accurate=True, optimizations=[]):
-    """adaptive_interpolation.py:14-34.  The adaptive fit is the reference's own CPU code."""
+    """Fit an adaptive interpolant of `func` on [a, b].  Pure delegation: the fit is the
+    reference's Interpolant.run_adapt + Approximator constructor, run unchanged on the CPU."""
     try:
-        import adaptive_interpolation.adapt as ref_adapt
-        import adaptive_interpolation.approximator as ref_app
+        from adaptive_interpolation import adapt as reference_adapt
+        from adaptive_interpolation import approximator as reference_approximator
     except ImportError:
         raise ImportError("make_interpolant runs the reference's CPU fitter (adaptive_interpolation.adapt), "
                           "which is not importable here; only evaluation is provided by this package")
-    with _numpy_compat():
-        my_adapt = ref_adapt.Interpolant(func, order, error, basis, dtype, accurate, optimizations=optimizations)
-        my_adapt.run_adapt(a, b, adapt_type)
-        approximation = ref_app.Approximator(my_adapt, optimizations=optimizations)
-    dt = int(dtype)
-    if dt <= 32:
-        approximation.dtype_name = "float"
-    elif dt <= 64:
-        approximation.dtype_name = "double"
-    elif dt <= 80:
-        approximation.dtype_name = "long double"
-    else:
-        raise Exception("Incorrect data type specified")
-    return approximation
+    name = _dtype_name(dtype) if int(dtype) <= 80 else None
+    with _integer_linspace_counts():
+        fitter = reference_adapt.Interpolant(func, order, error, basis, dtype, accurate,
+                                             optimizations=optimizations)
+        fitter.run_adapt(a, b, adapt_type)
+        table = reference_approximator.Approximator(fitter, optimizations=optimizations)
+    table.dtype_name = name if name is not None else _dtype_name(dtype)
+    return table
 
 
 def generate_code(approx, size=None, vector_width=1, cpu=False):
-    """adaptive_interpolation.py:37-75: same validation, same side effects.  The returned
-    "code" names the precompiled CUDA kernel that will evaluate this approximation."""
-    approx.vector_width = vector_width
-    approx.size = size
+    """Select the evaluator for `approx` and record it on the object.
+
+    Mirrors the reference's argument rules: the CPU (ISPC) flavour needs a size and a Chebyshev
+    basis; the device flavour needs `size` and a non-default `vector_width` together or not at
+    all.  Returns the text stored in approx.code."""
+    approx.vector_width, approx.size = vector_width, size
     if cpu:
         if size is None:
-            raise Exception("The size must be known to generate cpu code.")
-        if approx.basis != 'chebyshev':
-            string_err = "ISPC generation only compatible with "
-            string_err += "chebyshev interpolants currently."
-            raise Exception(string_err)
-        else:
-            code = generate.gen_ispc(approx)
+            raise Exception(_MSG_CPU_NEEDS_SIZE)
+        if approx.basis != "chebyshev":
+            raise Exception(_MSG_ISPC_CHEB_ONLY)
+        text = generate.gen_ispc(approx)
     else:
-        if ((vector_width != 1) and (size is None)) \
-                or ((vector_width == 1) and (size is not None)):
-            string_err = "Both vector width and domain_size must be given "
-            string_err += "if running single-threaded code."
-            raise Exception(string_err)
-        if approx.basis == 'monomial':
-            code = generate.gen_mono(approx)
-        elif approx.basis == 'chebyshev':
-            code = generate.gen_cheb(approx)
-        elif approx.basis == 'legendre':
-            code = generate.gen_leg(approx)
-        else:
-            raise Exception("Incorrect basis provided: monomial, chebyshev, legendre.")
-    approx.code = code
-    return code
+        width_given, size_given = vector_width != 1, size is not None
+        if width_given != size_given:
+            raise Exception(_MSG_WIDTH_AND_SIZE)
+        generator = _DEVICE_GENERATORS.get(approx.basis)
+        if generator is None:
+            raise Exception(_MSG_BAD_BASIS)
+        text = generator(approx)
+    approx.code = text
+    return text
 
 
 def write_to_file(file_path, approx):
-    """adaptive_interpolation.py:78-88."""
-    with open(file_path, 'wb') as f:
-        pickle.dump(approx, f, pickle.HIGHEST_PROTOCOL)
+    """Pickle the whole Approximator, as the reference does.  Works because this package never
+    parks device handles on the object."""
+    with open(file_path, "wb") as stream:
+        pickle.dump(approx, stream, pickle.HIGHEST_PROTOCOL)
 
 
 def load_from_file(file_path):
-    """adaptive_interpolation.py:91-105.  Also loads the saved tables when the reference package
-    (and the `__main__.f` they reference) is absent -- see approximator.load."""
+    """Unpickle a saved approximation.  Unlike the reference this also works when neither the
+    reference package nor the fitted function (`__main__.f`) exists in the process -- see
+    approximator.load.  Any failure surfaces as the reference's generic Exception."""
     try:
-        return app.load(file_path)
+        return _approximator.load(file_path)
     except Exception:
-        str_err = "Error loading instance from {0}".format(file_path)
-        raise Exception(str_err)
+        raise Exception(_MSG_LOAD_FAILED.format(file_path))
 
 
 def run_approximation(x, approx):
-    """adaptive_interpolation.py:111-123 -> (run_time, output)."""
+    """Evaluate `approx` at x -> (run_time, output).  run_time is the kernel-only device time in
+    seconds when generate_code recorded a vector width, else None (one-shot path)."""
     if approx.code == 0:
-        string_err = "Approximator class does not have any associated "
-        string_err += "code. Run a generate method to add code to the class."
-        raise Exception(string_err)
+        raise Exception(_MSG_NO_CODE)
     if approx.vector_width is None:
-        output = generate.run(x, approx)
-        run_time = None
-    else:
-        generate.build_code(approx)
-        run_time, output = generate.run_single(x, approx)
-    return run_time, output
+        return None, generate.run(x, approx)
+    generate.build_code(approx)
+    return generate.run_single(x, approx)
 
 
 def run_code(x, approx, vectorized=None):
-    """Legacy entry point (tests/generate_tests.py:26, performance_tests.py:98-107): returns
-    the output only."""
+    """Legacy entry point (tests/generate_tests.py:26, performance_tests.py:98-107): output only."""
     return run_approximation(x, approx)[1]
