@@ -22,6 +22,7 @@ import pickle
 import numpy as np
 
 from . import approximator as _approximator
+from . import fit as _fit
 from . import generate
 
 # --- message texts callers (and the reference's own tests) match on -------------------------------
@@ -73,7 +74,9 @@ def _integer_linspace_counts():
 def make_interpolant(a, b, func, order, error, basis="chebyshev",
                      adapt_type="Remez", dtype='64', accurate=True, optimizations=[]):
     """Fit an adaptive interpolant of `func` on [a, b].  Pure delegation: the fit is the
-    reference's Interpolant.run_adapt + Approximator constructor, run unchanged on the CPU."""
+    reference's Interpolant.run_adapt + Approximator constructor, run unchanged on the CPU.
+    Passing "gpu find_error" in `optimizations` (the reference's free-form flag list) evaluates
+    each node's candidate polynomial on the GPU instead of in the Python loop (fit.py)."""
     try:
         from adaptive_interpolation import adapt as reference_adapt
         from adaptive_interpolation import approximator as reference_approximator
@@ -84,6 +87,8 @@ def make_interpolant(a, b, func, order, error, basis="chebyshev",
     with _integer_linspace_counts():
         fitter = reference_adapt.Interpolant(func, order, error, basis, dtype, accurate,
                                              optimizations=optimizations)
+        if _fit.FLAG in optimizations:          # opt-in: GPU-evaluated find_error (fit.py)
+            _fit.accelerate(fitter)
         fitter.run_adapt(a, b, adapt_type)
         table = reference_approximator.Approximator(fitter, optimizations=optimizations)
     table.dtype_name = name if name is not None else _dtype_name(dtype)

@@ -41,6 +41,26 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                \
     } while (0)
 
+// cudaGetDeviceProperties costs milliseconds; tables can be created per fitter node (fit.py)
+struct DeviceInfo { bool known = false; int major = 0, minor = 0, sm_count = 0; size_t smem_optin = 0; };
+int device_info(int device, DeviceInfo* out) {
+    static std::mutex mu;
+    static DeviceInfo cache[64];
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 || device >= 64) return fail(AI_ERR_INVALID, "device %d out of range", device);
+    if (!cache[device].known) {
+        cudaDeviceProp prop;
+        cudaError_t e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) return fail(AI_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+        cache[device].known = true;
+        cache[device].major = prop.major; cache[device].minor = prop.minor;
+        cache[device].sm_count = prop.multiProcessorCount;
+        cache[device].smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+    }
+    *out = cache[device];
+    return AI_OK;
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -305,13 +325,14 @@ int finish_table(ai_table* t) {
 
     DeviceGuard guard(t->device);
     if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
-    cudaDeviceProp prop;
-    AI_CUDA(cudaGetDeviceProperties(&prop, t->device));
+    DeviceInfo prop;
+    rc = device_info(t->device, &prop);
+    if (rc) return rc;
     if (prop.major < 10)
         return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
                     t->device, prop.major, prop.minor);
-    t->sm_count = prop.multiProcessorCount;
-    const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
+    t->sm_count = prop.sm_count;
+    const size_t smem_cap = prop.smem_optin;
 
     // build the packed (shared-memory) image first; if it cannot be staged, rebuild it in the
     // global layout (16-byte padded records)

@@ -505,6 +505,43 @@ def test_exact_interpolants_like_the_reference_test():
         assert rel < max(4e-15, 2 * rel_ref), (name, rel, rel_ref)
 
 
+def test_gpu_assisted_find_error_reproduces_the_reference_fit():
+    """the opt-in GPU find_error yields the same tree and coefficients as the
+    reference's own fit.  Needs the reference fitter, which travels in baseline/_ref (the
+    unmodified reference installed with pip --target, git-ignored)."""
+    import contextlib
+    import io
+    import sys
+    import time
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "adaptive_interpolation")):
+        pytest.skip("baseline/_ref (reference fitter) not installed")
+    sys.path.insert(0, ref)
+    try:
+        cases = [(0, 10, lambda t: np.sin(np.sin(t)), 3, 1e-6, "chebyshev", "Trivial", "64"),
+                 (0, 10, lambda t: np.cos(np.sin(t)), 7, 1e-8, "legendre", "Trivial", "64"),
+                 (0, 20, lambda t: np.sin(np.sin(t)), 5, 1e-4, "chebyshev", "Trivial", "32")]
+        for a, b, fn, order, err, basis, kind, dt in cases:
+            times = []
+            fits = []
+            for opts in (["arrays", "map"], ["arrays", "map", "gpu find_error"]):
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    fits.append(adapt_i.make_interpolant(a, b, fn, order, err, basis, kind, dt, True, opts))
+                times.append(time.perf_counter() - t0)
+            ref_fit, gpu_fit = fits
+            assert np.array_equal(np.asarray(ref_fit.interval_a), np.asarray(gpu_fit.interval_a))
+            assert np.array_equal(np.asarray(ref_fit.interval_b), np.asarray(gpu_fit.interval_b))
+            assert np.array_equal(np.asarray(ref_fit.coeff), np.asarray(gpu_fit.coeff))
+            assert np.array_equal(ref_fit.tree_1d, gpu_fit.tree_1d)
+            report(test="gpu_find_error", basis=basis, order=order, dtype=dt, leaves=len(ref_fit.interval_a),
+                   seconds_reference=times[0], seconds_gpu_assisted=times[1])
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "adaptive_interpolation" or k.startswith("adaptive_interpolation.")]:
+            del sys.modules[k]
+
+
 def test_reference_parity_test_intent():
     """tests/generate_tests.py:27: ||app.evaluate(x) - run_code(x)||_inf / max|f| < 1e-12 (fp64)."""
     for name in ("gen__cossin_cheb_o10_f64", "gen__sinsin_leg_o10_f64", "gen__cfg1_sinsin_cheb_o3_f64"):
