@@ -33,8 +33,8 @@ namespace ai {
 #define AI_UNIFORM_PATH 2          // 0: off, 1: test every tile, 2: adaptive (re-probe every 16 tiles)
 #endif
 
-#ifndef AI_LEG_CLENSHAW
-#define AI_LEG_CLENSHAW 1          // Legendre-like basis: Clenshaw (3 instr/degree) vs forward (5)
+#ifndef AI_PACKED_F32
+#define AI_PACKED_F32 1            // fp32: two points per FFMA2 / FADD2 / FMUL2 (1: both paths, 2: leaf-uniform path only, 0: off)
 #endif
 // Debug build (tools/tune.py "debug_bounds"): every table access is range-checked and traps.
 #ifdef AI_DEBUG_BOUNDS
@@ -282,33 +282,67 @@ template <int BASIS, int ORDER, typename T> struct Record {
     }
 };
 
-// rec holds one leaf record.  Arithmetic follows the reference's operation order (adapt.py:97-139
-// as called from approximator.py:291-295) with each multiply-add pair fused; see DESIGN.md
-// "numerics" for the measured deviation from the reference evaluator.
-template <int BASIS, int ORDER, typename T>
-__device__ __forceinline__ T eval_record(const Record<BASIS, ORDER, T>& r, T x, T inv_order) {
+// Arithmetic on one value (float / double) or on a PAIR of floats held in a 64-bit register pair.
+// sm_100 issues packed FP32 operations (FFMA2 / FADD2 / FMUL2: two IEEE operations per issued
+// instruction, operand negation folded in), which halves the FP issue slots of the fp32 kernels;
+// every lane result is the same IEEE operation as the scalar form, so the bits are identical.
+template <typename V> struct Ops;
+template <> struct Ops<float> {
+    using S = float;
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float neg(float a) { return -a; }
+    static __device__ __forceinline__ float splat(float s) { return s; }
+};
+template <> struct Ops<double> {
+    using S = double;
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double neg(double a) { return -a; }
+    static __device__ __forceinline__ double splat(double s) { return s; }
+};
+template <> struct Ops<float2> {
+    using S = float;
+    static __device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+    static __device__ __forceinline__ float2 neg(float2 a) { return make_float2(-a.x, -a.y); }
+    static __device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+};
+
+// v holds one leaf record per lane of V: [a, 2/(b-a), c0..cn] ([c0..cn] for the monomial basis).
+// Arithmetic follows the reference's definitions (adapt.py:97-139 as called from
+// approximator.py:291-295) with each multiply-add pair fused; see DESIGN.md "numerics" for the
+// measured deviation from the reference evaluator.
+template <int BASIS, int ORDER, typename V>
+__device__ __forceinline__ V eval_values(const V* __restrict__ v, V x) {
+    using O = Ops<V>;
+    using S = typename O::S;
     if constexpr (BASIS == kMono) {
         // adapt.py:139 sum c_i x^i on the RAW x; Horner as generate.py:48-52
-        T acc = r.v[ORDER];
+        V acc = v[ORDER];
 #pragma unroll
-        for (int j = ORDER - 1; j >= 0; --j) acc = fma_(acc, x, r.v[j]);
+        for (int j = ORDER - 1; j >= 0; --j) acc = O::fma(acc, x, v[j]);
         return acc;
     } else {
-        const T a = r.v[0], s = r.v[1];
-        const T* c = r.v + 2;
+        const V* c = v + 2;
         // adapt.py:130  xscaled = 2*(x-a)/(b-a) - 1, with 2/(b-a) precomputed per leaf in T
-        const T t = fma_(x - a, s, (T)-1);
+        const V t = O::fma(O::add(x, O::neg(v[0])), v[1], O::splat((S)-1));
         if constexpr (ORDER == 0) {
             return c[0];
+        } else if constexpr (ORDER == 1) {
+            return O::fma(c[1], t, c[0]);
         } else if constexpr (BASIS == kCheb) {
             // adapt.py:111-120  T0=1, T1=t, Ti = (2t) T(i-1) - T(i-2);  y = sum c_i T_i
-            const T t2 = t + t;
-            T acc = fma_(c[1], t, c[0]);
-            T p0 = (T)1, p1 = t;
+            const V t2 = O::add(t, t);
+            V acc = O::fma(c[1], t, c[0]);
+            V p0 = O::splat((S)1), p1 = t;
 #pragma unroll
             for (int j = 2; j <= ORDER; ++j) {
-                const T pn = fma_(t2, p1, -p0);
-                acc = fma_(c[j], pn, acc);
+                const V pn = O::fma(t2, p1, O::neg(p0));
+                acc = O::fma(c[j], pn, acc);
                 p0 = p1; p1 = pn;
             }
             return acc;
@@ -316,43 +350,42 @@ __device__ __forceinline__ T eval_record(const Record<BASIS, ORDER, T>& r, T x, 
             // adapt.py:97-108  L0=1, L1=t, Li = ((2i-1) t L(i-1) + (i-1) L(i-2)) * (1./n)
             // -- note the PLUS sign and the constant divisor n: this is the reference's basis,
             // not the Legendre polynomials; the saved coefficients were fitted in it.
-            if constexpr (ORDER == 1) {
-                return fma_(c[1], t, c[0]);
-            } else {
-#if AI_LEG_CLENSHAW
-                // Clenshaw for L_k = (al_k t) L_(k-1) + be_k L_(k-2), al_k = (2k-1)/n, be_k = (k-1)/n:
-                //   b_k = c_k + (al_(k+1) t) b_(k+1) + be_(k+2) b_(k+2),  k = n..2
-                //   y   = c0 + c1 t + b_2 L_2 + (be_3 b_3) t
-                // 3 instructions per degree instead of the forward form's 5; measured within 2.1
-                // units of eps*error_scale of the reference evaluator (forward: 1.7).
-                constexpr double dn = (double)ORDER;
-                T b1 = c[ORDER], b2 = (T)0;
+            // Clenshaw for L_k = (al_k t) L_(k-1) + be_k L_(k-2), al_k = (2k-1)/n, be_k = (k-1)/n:
+            //   b_k = c_k + (al_(k+1) t) b_(k+1) + be_(k+2) b_(k+2),  k = n..2
+            //   y   = c0 + c1 t + b_2 L_2 + (be_3 b_3) t
+            // 3 instructions per degree instead of the forward form's 5; measured within 2.1
+            // units of eps*error_scale of the reference evaluator (forward: 1.7).
+            constexpr double dn = (double)ORDER;
+            V b1 = c[ORDER], b2 = O::splat((S)0);
 #pragma unroll
-                for (int k = ORDER - 1; k >= 2; --k) {
-                    const T al = (T)((2.0 * (k + 1) - 1.0) / dn), be = (T)(((k + 2) - 1.0) / dn);
-                    const T bk = fma_(al * t, b1, fma_(be, b2, c[k]));
-                    b2 = b1; b1 = bk;
-                }
-                const T al2 = (T)(3.0 / dn), be2 = (T)(1.0 / dn), be3 = (T)(2.0 / dn);
-                const T l2 = fma_(al2 * t, t, be2);
-                T acc = fma_(c[1], t, c[0]);
-                acc = fma_(b1, l2, acc);
-                return fma_(be3 * b2, t, acc);
-#else
-                T acc = fma_(c[1], t, c[0]);
-                T p0 = (T)1, p1 = t;
-#pragma unroll
-                for (int j = 2; j <= ORDER; ++j) {
-                    const T first = ((T)(2 * j - 1) * t);
-                    const T pn = fma_(first, p1, (T)(j - 1) * p0) * inv_order;
-                    acc = fma_(c[j], pn, acc);
-                    p0 = p1; p1 = pn;
-                }
-                return acc;
-#endif
+            for (int k = ORDER - 1; k >= 2; --k) {
+                const S al = (S)((2.0 * (k + 1) - 1.0) / dn), be = (S)(((k + 2) - 1.0) / dn);
+                const V bk = O::fma(O::mul(O::splat(al), t), b1, O::fma(O::splat(be), b2, c[k]));
+                b2 = b1; b1 = bk;
             }
+            const S al2 = (S)(3.0 / dn), be2 = (S)(1.0 / dn), be3 = (S)(2.0 / dn);
+            const V l2 = O::fma(O::mul(O::splat(al2), t), t, O::splat(be2));
+            V acc = O::fma(c[1], t, c[0]);
+            acc = O::fma(b1, l2, acc);
+            return O::fma(O::mul(O::splat(be3), b2), t, acc);
         }
     }
+}
+
+template <int BASIS, int ORDER, typename T>
+__device__ __forceinline__ T eval_record(const Record<BASIS, ORDER, T>& r, T x, T /*inv_order*/) {
+    return eval_values<BASIS, ORDER, T>(r.v, x);
+}
+
+// two fp32 points, each with its own leaf record, per issued instruction
+template <int BASIS, int ORDER>
+__device__ __forceinline__ float2 eval_record_pair(const Record<BASIS, ORDER, float>& ra,
+                                                   const Record<BASIS, ORDER, float>& rb, float xa, float xb) {
+    constexpr int N = Record<BASIS, ORDER, float>::N;
+    float2 v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = make_float2(ra.v[k], rb.v[k]);
+    return eval_values<BASIS, ORDER, float2>(v, make_float2(xa, xb));
 }
 
 template <int BASIS, int ORDER, typename T, int STRIDE = 1, bool VEC = false>
@@ -504,14 +537,33 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
         if (uniform) {
             Record<BASIS, ORDER, T> rec;
             load_record(rec, li[0]);
+            if constexpr (sizeof(T) == 4 && AI_PACKED_F32) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+                for (int e = 0; e < NE; e += 2) {
+                    const float2 r2 = eval_record_pair<BASIS, ORDER>(rec, rec, xs[e], xs[e + 1]);
+                    xs[e] = r2.x; xs[e + 1] = r2.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+            }
         } else {
+            if constexpr (sizeof(T) == 4 && AI_PACKED_F32 == 1) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                Record<BASIS, ORDER, T> rec;
-                load_record(rec, li[e]);
-                xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+                for (int e = 0; e < NE; e += 2) {
+                    Record<BASIS, ORDER, T> ra, rb;
+                    load_record(ra, li[e]);
+                    load_record(rb, li[e + 1]);
+                    const float2 r2 = eval_record_pair<BASIS, ORDER>(ra, rb, xs[e], xs[e + 1]);
+                    xs[e] = r2.x; xs[e + 1] = r2.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    Record<BASIS, ORDER, T> rec;
+                    load_record(rec, li[e]);
+                    xs[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+                }
             }
         }
 #pragma unroll

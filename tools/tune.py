@@ -14,16 +14,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
+    # tag: defines   (defaults: AI_BLOCK=512 AI_UNROLL=6 AI_UNROLL_F64=5 AI_PREFETCH=1 AI_UNIFORM_PATH=2 AI_PACKED_F32=1)
     "debug_bounds": ["AI_DEBUG_BOUNDS=1"],
-    # tag: defines   (defaults: AI_BLOCK=512 AI_UNROLL=4 AI_PREFETCH=1 AI_UNIFORM_PATH=2 AI_MIN_BLOCKS=1)
-    "t512_u6": ["AI_UNROLL=6", "AI_UNROLL_F64=6"],
-    "t768_u6": ["AI_BLOCK=768", "AI_UNROLL=6", "AI_UNROLL_F64=6"],
-    "t512_u7": ["AI_UNROLL=7", "AI_UNROLL_F64=7"],
-    "t640_u6": ["AI_BLOCK=640", "AI_UNROLL=6", "AI_UNROLL_F64=6"],
-    "t768_u5": ["AI_BLOCK=768", "AI_UNROLL=5", "AI_UNROLL_F64=5"],
-    "t640_u5": ["AI_BLOCK=640", "AI_UNROLL=5", "AI_UNROLL_F64=5"],
-    "t512_u5": ["AI_UNROLL=5", "AI_UNROLL_F64=5"],
-    "t512_u6_c0": ["AI_UNROLL=6", "AI_UNROLL_F64=6", "AI_UNIFORM_PATH=0"],
+    "packed_uniform_only": ["AI_PACKED_F32=2"],
+    "packed_off": ["AI_PACKED_F32=0"],
 }
 TABLES = ("approx__32o6-p1.19209289551e-06,approx__32o13-p1.19209289551e-06,gen__cfg3_j0_cheb_o13_f64,"
           "approx__64o7-p2.22044604925e-14,approx__64o6-p1.19209289551e-06,approx__32o3-p1.19209289551e-06")
