@@ -115,6 +115,7 @@ struct ai_table {
     int copies = 1;                    // bank modes: copies per element
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
+    std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
     HostPipe pipe;
 };
 
@@ -374,6 +375,20 @@ int finish_table(ai_table* t) {
         }
     }
     if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
+    // two leaves: both records ride in the kernel parameters, element-wise select instead of a gather
+    if (!go_global && ((L == 2 && forced < 0) || (L <= 2 && forced == ai::kSelect))) {
+        mode = ai::kSelect; copies = 1;
+        const int nrec = t->order + 1 + ((t->basis == ai::kMono) ? 0 : 2);
+        t->select.assign(1 + 2 * ai::kMaxRecord, 0.0);
+        t->select[0] = (L == 2) ? t->breaks[1] : std::numeric_limits<double>::infinity();
+        for (int i = 0; i < 2; ++i) {
+            const int64_t leaf = std::min<int64_t>(i, L - 1);
+            const unsigned char* rec = image.data() + t->view.off_records + (size_t)leaf * t->rstride * esz;
+            for (int k = 0; k < nrec; ++k)
+                t->select[1 + i * ai::kMaxRecord + k] = (t->dtype == AI_DTYPE_F32)
+                    ? (double)reinterpret_cast<const float*>(rec)[k] : reinterpret_cast<const double*>(rec)[k];
+        }
+    }
     t->mode = mode;
     t->copies = copies;
     t->view.copies = copies;
@@ -448,6 +463,7 @@ int launch_eval_t(const ai_table* t, const T* x, T* y, int64_t n, cudaStream_t s
     cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
     cfg.smem_bytes = t->eval_smem;
     cfg.stream = stream;
+    cfg.select = t->select.empty() ? nullptr : t->select.data();
     cudaError_t e;
     const int m = t->mode;
     if constexpr (sizeof(T) == 4) {
@@ -514,6 +530,7 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * t->blocks_per_sm));
     cfg.smem_bytes = t->aux_smem;
     cfg.stream = s;
+    cfg.select = nullptr;
     cudaError_t e;
     const int m = (t->mode == ai::kGlobal) ? ai::kGlobal : ai::kSmem;
     if constexpr (sizeof(T) == 4) {

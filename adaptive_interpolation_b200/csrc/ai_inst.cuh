@@ -13,11 +13,20 @@ template <int BASIS, typename T, int ORDER, int MODE>
 struct Unit {
     static cudaError_t eval(const LaunchCfg& c, const TableView& tv, const T* x, T* y,
                             long long n, long long head, long long nvec) {
-        eval_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, y, n, head, nvec);
+        SelectTable<T, MODE> sel;
+        if constexpr (MODE == kSelect) {
+            if (!c.select) return cudaErrorInvalidValue;
+            sel.mid = (T)c.select[0];
+            for (int k = 0; k < kMaxRecord; ++k) {
+                sel.rec[0][k] = (T)c.select[1 + k];
+                sel.rec[1][k] = (T)c.select[1 + kMaxRecord + k];
+            }
+        }
+        eval_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, sel, x, y, n, head, nvec);
         return cudaGetLastError();
     }
     static cudaError_t sum(const LaunchCfg& c, const TableView& tv, const T* x, double* r, long long n) {
-        if constexpr (MODE == kSmemBank || MODE == kSmemBankN) {
+        if constexpr (MODE == kSmemBank || MODE == kSmemBankN || MODE == kSelect) {
             return cudaErrorInvalidValue;
         } else {
             eval_sum_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, r, n);
@@ -50,6 +59,7 @@ struct Switch {
             if (mode == kSmemBank) return Unit<BASIS, T, ORDER, kSmemBank>::eval(a...);
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::eval(a...);
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::eval(a...);
+            if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::eval(a...);
             return cudaErrorInvalidValue;
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::eval(order, mode, a...);
@@ -69,6 +79,7 @@ struct Switch {
             if (mode == kSmemBank) return Unit<BASIS, T, ORDER, kSmemBank>::prepare(smem_bytes, bps);
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::prepare(smem_bytes, bps);
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::prepare(smem_bytes, bps);
+            if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::prepare(smem_bytes, bps);
             return cudaErrorInvalidValue;
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::prepare(order, mode, smem_bytes, bps);

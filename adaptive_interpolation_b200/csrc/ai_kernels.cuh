@@ -66,8 +66,22 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              the global image (tables too large for shared memory)
 //   kSmemBankN as kSmemBank with a run-time power-of-two copy count < 32 (16): tables whose full
 //              replication does not fit in shared memory (lanes l mod N share a copy)
+//   kSelect    tables with at most TWO leaves (the saved order-13 tables): nothing staged and no
+//              gather at all.  Both records travel in the kernel parameter space (constant
+//              bank), the leaf is the predicate !(x < mid) and every record element is a
+//              register/constant SELECT, which runs on the ALU pipe instead of the 128 B/clk
+//              shared-memory return path that bounds random points at high order
+//              (tools/micro/shfl_bench.cu: LDS and SHFL share that path, LDC does not but
+//              serialises per distinct address).
 // In both bank modes the breakpoint array read by the search is replicated the same way.
-enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3 };
+enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4 };
+constexpr int kMaxRecord = 16 + 1 + 2;         // AI_MAX_ORDER + 1 coefficients + [a, 2/(b-a)]
+// kSelect's table, passed by value as a kernel parameter; empty in every other mode
+template <typename T, int MODE> struct SelectTable {};
+template <typename T> struct SelectTable<T, kSelect> {
+    T mid;                          // breaks[1]; +inf for a single-leaf table
+    T rec[2][kMaxRecord];           // [a, 2/(b-a), c0..cn] ([c0..cn] for the monomial basis)
+};
 template <typename T, int MODE> struct Copies {
     static constexpr int value = (MODE == kSmemBank) ? (sizeof(T) == 4 ? 32 : 16) : 1;
 };
@@ -405,7 +419,7 @@ template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v
 // element once per bank.  kGlobal: nothing to do.
 template <typename T, int MODE>
 __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
-    if constexpr (MODE == kGlobal) {
+    if constexpr (MODE == kGlobal || MODE == kSelect) {
         return tv.image;
     } else if constexpr (MODE == kSmem) {
         const int4* src = reinterpret_cast<const int4*>(tv.image);
@@ -437,7 +451,7 @@ __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, 
 // to each other, in which case head == n and everything takes the scalar loop.
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock, AI_MIN_BLOCKS)
-eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
+eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restrict__ x, T* __restrict__ y,
             long long n, long long head, long long nvec) {
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned char* base = table_base<T, MODE>(tv, smem);
@@ -457,15 +471,31 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
 
     auto load_record = [&](Record<BASIS, ORDER, T>& r, int leaf) {
         AI_CHECK(leaf >= 0 && leaf < tv.n_leaves);
-        const T* p = records + leaf * R;
-        if constexpr (VEC) r.load_vec(p);
-        else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);
-        else if constexpr (MODE == kSmemBankN) r.load_strided(p, cp);
-        else r.template load<1>(p);
+        if constexpr (MODE == kSelect) {
+#pragma unroll
+            for (int k = 0; k < Record<BASIS, ORDER, T>::N; ++k) r.v[k] = leaf ? sel.rec[1][k] : sel.rec[0][k];
+        } else {
+            const T* p = records + leaf * R;
+            if constexpr (VEC) r.load_vec(p);
+            else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);
+            else if constexpr (MODE == kSmemBankN) r.load_strided(p, cp);
+            else r.template load<1>(p);
+        }
+    };
+    // leaf ordinals of the NE points of a tile.  kSelect: #{k: breaks[k] <= x} - 1 clamped to
+    // {0, 1} is the single predicate !(x < mid) (NaN -> 1 = the last leaf, as the BST walk).
+    auto find_leaves = [&](const auto& xs, auto& li) {
+        if constexpr (MODE == kSelect) {
+#pragma unroll
+            for (int e = 0; e < (int)(sizeof(li) / sizeof(li[0])); ++e) li[e] = !(xs[e] < sel.mid) ? 1 : 0;
+        } else {
+            lk.leaves(xs, li);
+        }
     };
     auto f = [&](T xv) -> T {
         Record<BASIS, ORDER, T> r;
-        load_record(r, lk.leaf(xv));
+        if constexpr (MODE == kSelect) load_record(r, !(xv < sel.mid) ? 1 : 0);
+        else load_record(r, lk.leaf(xv));
         return eval_record<BASIS, ORDER, T>(r, xv, inv_order);
     };
 
@@ -511,7 +541,7 @@ eval_kernel(const TableView tv, const T* __restrict__ x, T* __restrict__ y,
                 xs[2 * u] = in[u].x; xs[2 * u + 1] = in[u].y;
             }
         }
-        lk.template leaves<NE>(xs, li);
+        find_leaves(xs, li);
         // Sorted / clustered inputs: all NE points of this thread usually sit in one leaf.  When
         // that holds for every lane of the warp, load the record ONCE into registers (n+3 shared
         // loads per NE points instead of per point).  Same arithmetic, so the bits are the same.
@@ -651,6 +681,7 @@ struct LaunchCfg {
     int grid;
     int smem_bytes;
     cudaStream_t stream;
+    const double* select;          // kSelect only: host array [mid, rec0[kMaxRecord], rec1[kMaxRecord]]
 };
 
 // One translation unit per (basis, dtype) -- see ai_inst.cuh -- each exporting:

@@ -162,15 +162,19 @@ def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
     """Packed shared memory / bank-private shared memory (full or partial replication) / global
-    (L2-resident): same leaf, same arithmetic, so identical indices and value bits on every table."""
+    (L2-resident) / two-leaf select from the kernel parameters: same leaf, same arithmetic, so
+    identical indices and value bits on every table."""
     g = golden(name)
     want_y = gpu_eval(dev_table(name), g.x)
     monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
     tab = dev_table(name)
     info = tab.info()
+    if mode == 4 and info["n_leaves"] > 2:
+        assert info["residency"] != 4
+        pytest.skip("select mode serves tables with at most two leaves")
     if mode == 1 and info["residency"] != 1:
         # 32 (16) copies of the records do not fit in 227 KB: the library keeps its own choice
         assert info["n_leaves"] * info["record_stride"] * 128 + info["image_bytes"] > 200 * 1024
@@ -312,7 +316,7 @@ def test_saved_tables_need_no_search():
     for name in SAVED:
         info = dev_table(name).info()
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1, 3)
+        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1, 3, 4)
     for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
         assert dev_table(name).info()["search_steps"] >= 1
 
