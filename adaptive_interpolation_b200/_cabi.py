@@ -17,6 +17,7 @@ AI_OK = 0
 BASIS_IDS = {"chebyshev": 0, "legendre": 1, "monomial": 2}
 DTYPE_F32, DTYPE_F64 = 0, 1
 MAX_ORDER = 16
+MAX_MULTI = 4
 
 # every symbol include/ai_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -24,7 +25,8 @@ EXPORTS = [
     "ai_table_create", "ai_table_create_from_tree", "ai_table_destroy", "ai_table_get_info",
     "ai_table_get_flat",
     "ai_eval_f32", "ai_eval_f64", "ai_eval_index_f32", "ai_eval_index_f64",
-    "ai_eval_sum_f32", "ai_eval_sum_f64", "ai_eval_host_f32", "ai_eval_host_f64",
+    "ai_eval_sum_f32", "ai_eval_sum_f64", "ai_eval_multi_f32", "ai_eval_multi_f64",
+    "ai_eval_host_f32", "ai_eval_host_f64",
     "ai_host_alloc", "ai_host_free", "ai_measure_fma_peak", "ai_copy_f32",
 ]
 
@@ -79,6 +81,9 @@ def lib():
     for name in ("ai_eval_f32", "ai_eval_f64", "ai_eval_index_f32", "ai_eval_index_f64",
                  "ai_eval_sum_f32", "ai_eval_sum_f64"):
         getattr(L, name).argtypes = [vp, vp, vp, i64, vp]
+    for name in ("ai_eval_multi_f32", "ai_eval_multi_f64"):
+        getattr(L, name).argtypes = [ctypes.POINTER(vp), i32, vp, ctypes.POINTER(vp), i64, vp,
+                                     ctypes.POINTER(ctypes.c_int)]
     for name in ("ai_eval_host_f32", "ai_eval_host_f64"):
         getattr(L, name).argtypes = [vp, vp, vp, i64, ctypes.POINTER(ctypes.c_double)]
     L.ai_host_alloc.argtypes = [ctypes.POINTER(vp), i64]

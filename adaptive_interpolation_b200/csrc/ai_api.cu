@@ -492,6 +492,83 @@ int eval_entry(const ai_table* t, const T* x, T* y, int64_t n, void* stream) {
     return launch_eval_t<T>(t, x, y, n, static_cast<cudaStream_t>(stream));
 }
 
+// Several tables, one pass over x.  Fused when every table can be staged
+// packed into shared memory next to the others and all share basis / order; otherwise the same
+// result comes from one single-table launch per table on the same stream.
+template <typename T>
+int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int64_t n, void* stream, int* fused_out) {
+    if (fused_out) *fused_out = 0;
+    if (!tabs || !y) return fail(AI_ERR_INVALID, "tables or y is NULL");
+    if (m < 1 || m > ai::kMaxMulti) return fail(AI_ERR_INVALID, "m = %d not in [1, %d]", m, ai::kMaxMulti);
+    if (n < 0) return fail(AI_ERR_INVALID, "n = %lld is negative", (long long)n);
+    for (int j = 0; j < m; ++j) {
+        if (!tabs[j]) return fail(AI_ERR_INVALID, "table %d is NULL", j);
+        if ((sizeof(T) == 4) != (tabs[j]->dtype == AI_DTYPE_F32))
+            return fail(AI_ERR_DTYPE, "table %d: dtype does not match the entry point", j);
+        if (tabs[j]->device != tabs[0]->device)
+            return fail(AI_ERR_INVALID, "table %d lives on device %d, table 0 on device %d", j, tabs[j]->device, tabs[0]->device);
+        if (n > 0 && !y[j]) return fail(AI_ERR_INVALID, "y[%d] is NULL", j);
+        for (int i = 0; i < j; ++i)
+            if (n > 0 && y[i] == y[j]) return fail(AI_ERR_INVALID, "y[%d] and y[%d] are the same buffer", i, j);
+    }
+    if (n == 0) return AI_OK;
+    if (!x) return fail(AI_ERR_INVALID, "x is NULL");
+    const ai_table* t0 = tabs[0];
+    DeviceGuard guard(t0->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t0->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    DeviceInfo prop;
+    int rc = device_info(t0->device, &prop);
+    if (rc) return rc;
+    const uintptr_t ax = reinterpret_cast<uintptr_t>(x);
+    bool fuse = (m >= 2) && !std::getenv("AI_B200_NO_FUSED_MULTI") && (ax % sizeof(T)) == 0;
+    size_t smem = 0;
+    ai::MultiArgs args{};
+    for (int j = 0; j < m && fuse; ++j) {
+        const ai_table* t = tabs[j];
+        fuse = t->basis == t0->basis && t->order == t0->order && (t->mode == ai::kSmem || t->mode == ai::kSelect)
+               && (reinterpret_cast<uintptr_t>(y[j]) % 16) == (ax % 16);
+        args.tv[j] = t->view;
+        args.y[j] = y[j];
+        args.soff[j] = (int)smem;
+        smem += (size_t)t->view.image_bytes;          // multiple of 16
+    }
+    fuse = fuse && smem <= prop.smem_optin;
+    if (!fuse) {
+        for (int j = 0; j < m; ++j) {
+            rc = launch_eval_t<T>(tabs[j], x, y[j], n, s);
+            if (rc) return rc;
+        }
+        return AI_OK;
+    }
+    args.m = m;
+    constexpr int VN = ai::Vec<T>::N;
+    long long head = (long long)(((16 - (ax % 16)) % 16) / sizeof(T));
+    if (head > n) head = n;
+    const long long nvec = (n - head) / VN;
+    ai::LaunchCfg cfg;
+    const long long tile_elems = (long long)ai::kBlock * ai::UnrollMulti<T>::value * VN;
+    const long long want = (n + tile_elems - 1) / tile_elems;
+    cfg.grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t0->sm_count));
+    cfg.smem_bytes = (int)smem;
+    cfg.stream = s;
+    cfg.select = nullptr;
+    cudaError_t e;
+    if constexpr (sizeof(T) == 4) {
+        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f32(t0->order, cfg, args, x, n, head, nvec);
+        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f32(t0->order, cfg, args, x, n, head, nvec);
+        else e = ai::launch_multi_mono_f32(t0->order, cfg, args, x, n, head, nvec);
+    } else {
+        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f64(t0->order, cfg, args, x, n, head, nvec);
+        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f64(t0->order, cfg, args, x, n, head, nvec);
+        else e = ai::launch_multi_mono_f64(t0->order, cfg, args, x, n, head, nvec);
+    }
+    if (e != cudaSuccess) return fail(AI_ERR_CUDA, "multi-table kernel launch failed: %s", cudaGetErrorString(e));
+    if (fused_out) *fused_out = 1;
+    return AI_OK;
+}
+
 template <typename T>
 int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* stream) {
     if (!t) return fail(AI_ERR_INVALID, "table handle is NULL");
@@ -833,6 +910,12 @@ int ai_eval_index_f32(const ai_table_t* t, const float* x, int32_t* i, int64_t n
 int ai_eval_index_f64(const ai_table_t* t, const double* x, int32_t* i, int64_t n, void* s) { return index_entry<double>(t, x, i, n, s); }
 int ai_eval_sum_f32(const ai_table_t* t, const float* x, double* r, int64_t n, void* s) { return sum_entry<float>(t, x, r, n, s); }
 int ai_eval_sum_f64(const ai_table_t* t, const double* x, double* r, int64_t n, void* s) { return sum_entry<double>(t, x, r, n, s); }
+int ai_eval_multi_f32(const ai_table_t* const* t, int m, const float* x, float* const* y, int64_t n, void* s, int* fused) {
+    return multi_entry<float>(t, m, x, y, n, s, fused);
+}
+int ai_eval_multi_f64(const ai_table_t* const* t, int m, const double* x, double* const* y, int64_t n, void* s, int* fused) {
+    return multi_entry<double>(t, m, x, y, n, s, fused);
+}
 int ai_eval_host_f32(const ai_table_t* t, const float* x, float* y, int64_t n, double* ms) { return host_entry<float>(t, x, y, n, ms); }
 int ai_eval_host_f64(const ai_table_t* t, const double* x, double* y, int64_t n, double* ms) { return host_entry<double>(t, x, y, n, ms); }
 

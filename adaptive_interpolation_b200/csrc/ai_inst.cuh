@@ -33,6 +33,16 @@ struct Unit {
             return cudaGetLastError();
         }
     }
+    static cudaError_t multi(const LaunchCfg& c, const MultiArgs& a, const T* x, long long n, long long head,
+                             long long nvec) {
+        if (c.smem_bytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(eval_multi_kernel<BASIS, ORDER, T>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+            if (e != cudaSuccess) return e;
+        }
+        eval_multi_kernel<BASIS, ORDER, T><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(a, x, n, head, nvec);
+        return cudaGetLastError();
+    }
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
         cudaError_t e;
         if (smem_bytes > 48 * 1024) {
@@ -73,6 +83,11 @@ struct Switch {
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::sum(order, mode, a...);
         else return cudaErrorInvalidValue;
     }
+    template <typename... A> static cudaError_t multi(int order, A&&... a) {
+        if (order == ORDER) return Unit<BASIS, T, ORDER, kSmem>::multi(a...);
+        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::multi(order, a...);
+        else return cudaErrorInvalidValue;
+    }
     static cudaError_t prepare(int order, int mode, int smem_bytes, int* bps) {
         if (order == ORDER) {
             if (mode == kSmem) return Unit<BASIS, T, ORDER, kSmem>::prepare(smem_bytes, bps);
@@ -99,6 +114,10 @@ struct Switch {
     cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv,   \
                                   const T* x, double* r, long long n) {                           \
         return Switch<BASIS, T>::sum(order, mode, c, tv, x, r, n);                                \
+    }                                                                                             \
+    cudaError_t launch_multi_##NAME(int order, const LaunchCfg& c, const MultiArgs& a, const T* x, \
+                                    long long n, long long head, long long nvec) {                \
+        return Switch<BASIS, T>::multi(order, c, a, x, n, head, nvec);                            \
     }                                                                                             \
     cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* bps) {                   \
         return Switch<BASIS, T>::prepare(order, mode, smem_bytes, bps);                           \

@@ -628,6 +628,161 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     for (long long k = head + nvec * VN + gtid; k < n; k += gstride) y[k] = f(x[k]);
 }
 
+// Several tables over the SAME x in one pass (the step after the path --
+// e.g. J0, J1, Y0, Y1 of one argument).  x is read once and m outputs are written:
+// (1 + m) * sizeof(T) bytes per point instead of 2 * m * sizeof(T) for m separate launches.
+// All tables share basis / order / dtype (one fit setting for several functions); every image is
+// staged packed into shared memory (the host falls back to per-table launches otherwise).  Per
+// table the lookup, record loads and arithmetic are those of eval_kernel<..., kSmem>, so every
+// output is bit-identical to the single-table result.
+constexpr int kMaxMulti = 4;
+#ifndef AI_UNROLL_MULTI
+#define AI_UNROLL_MULTI 6          // 16-byte vectors per thread per tile (measured best of 4, 5, 6)
+#endif
+#ifndef AI_UNROLL_MULTI_F64
+#define AI_UNROLL_MULTI_F64 4      // measured best of 3, 4, 5
+#endif
+template <typename T> struct UnrollMulti { static constexpr int value = AI_UNROLL_MULTI; };
+template <> struct UnrollMulti<double> { static constexpr int value = AI_UNROLL_MULTI_F64; };
+
+struct MultiArgs {
+    TableView tv[kMaxMulti];
+    void* y[kMaxMulti];
+    int soff[kMaxMulti];           // byte offset of table j's image in shared memory (16-byte aligned)
+    int m;
+};
+
+template <int BASIS, int ORDER, typename T>
+__global__ void __launch_bounds__(kBlock, 1)
+eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ x,
+                  long long n, long long head, long long nvec) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int m = args.m;
+    for (int j = 0; j < m; ++j) {
+        const int4* src = reinterpret_cast<const int4*>(args.tv[j].image);
+        int4* dst = reinterpret_cast<int4*>(smem + args.soff[j]);
+        for (int k = threadIdx.x; k < args.tv[j].image_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    __syncthreads();
+
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    constexpr int U = UnrollMulti<T>::value;
+    constexpr long long kTile = (long long)kBlock * U;
+    constexpr int NE = U * VN;
+    constexpr int R = rec_stride(BASIS, ORDER);
+    const V* __restrict__ xv = reinterpret_cast<const V*>(x + head);
+    const long long full_tiles = nvec / kTile;
+
+    auto load_tile = [&](V (&buf)[U], long long tile) {
+        const long long base = tile * kTile + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u) buf[u] = ld_stream(xv + base + (long long)u * kBlock);
+    };
+    auto scalar = [&](int j, T xs) -> T {
+        Lookup<T> lk;
+        lk.init(args.tv[j], smem + args.soff[j]);
+        const T* records = reinterpret_cast<const T*>(smem + args.soff[j] + args.tv[j].off_records);
+        return eval_leaf<BASIS, ORDER, T>(records + lk.leaf(xs) * R, xs, (T)0);
+    };
+
+    long long tile = blockIdx.x;
+    V in[U];
+    if (tile < full_tiles) load_tile(in, tile);
+    for (; tile < full_tiles; tile += gridDim.x) {
+        V nxt[U];
+        const long long next = tile + gridDim.x;
+        if (next < full_tiles) load_tile(nxt, next);
+        const long long base = tile * kTile + threadIdx.x;
+        T xs[NE];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if constexpr (VN == 4) {
+                xs[4 * u] = in[u].x; xs[4 * u + 1] = in[u].y; xs[4 * u + 2] = in[u].z; xs[4 * u + 3] = in[u].w;
+            } else {
+                xs[2 * u] = in[u].x; xs[2 * u + 1] = in[u].y;
+            }
+        }
+        for (int j = 0; j < m; ++j) {
+            Lookup<T> lk;
+            lk.init(args.tv[j], smem + args.soff[j]);
+            const T* records = reinterpret_cast<const T*>(smem + args.soff[j] + args.tv[j].off_records);
+            int li[NE];
+            lk.template leaves<NE>(xs, li);
+            bool same = true;
+#pragma unroll
+            for (int e = 1; e < NE; ++e) same = same && (li[e] == li[0]);
+            const bool uniform = __all_sync(0xffffffffu, same);
+            T ys[NE];
+            if (uniform) {
+                Record<BASIS, ORDER, T> rec;
+                rec.template load<1>(records + li[0] * R);
+                if constexpr (sizeof(T) == 4 && AI_PACKED_F32) {
+#pragma unroll
+                    for (int e = 0; e < NE; e += 2) {
+                        const float2 r2 = eval_record_pair<BASIS, ORDER>(rec, rec, xs[e], xs[e + 1]);
+                        ys[e] = r2.x; ys[e + 1] = r2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) ys[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], (T)0);
+                }
+            } else {
+                if constexpr (sizeof(T) == 4 && AI_PACKED_F32 == 1) {
+#pragma unroll
+                    for (int e = 0; e < NE; e += 2) {
+                        Record<BASIS, ORDER, T> ra, rb;
+                        ra.template load<1>(records + li[e] * R);
+                        rb.template load<1>(records + li[e + 1] * R);
+                        const float2 r2 = eval_record_pair<BASIS, ORDER>(ra, rb, xs[e], xs[e + 1]);
+                        ys[e] = r2.x; ys[e + 1] = r2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        Record<BASIS, ORDER, T> rec;
+                        rec.template load<1>(records + li[e] * R);
+                        ys[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], (T)0);
+                    }
+                }
+            }
+            V* __restrict__ yv = reinterpret_cast<V*>(static_cast<T*>(args.y[j]) + head);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                V out;
+                if constexpr (VN == 4) {
+                    out.x = ys[4 * u]; out.y = ys[4 * u + 1]; out.z = ys[4 * u + 2]; out.w = ys[4 * u + 3];
+                } else {
+                    out.x = ys[2 * u]; out.y = ys[2 * u + 1];
+                }
+                st_stream(yv + base + (long long)u * kBlock, out);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) in[u] = nxt[u];
+    }
+    // remainder vectors, then the scalar head and tail
+    const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kBlock;
+    for (long long v = full_tiles * kTile + gtid; v < nvec; v += gstride) {
+        const V inv = ld_stream(xv + v);
+        for (int j = 0; j < m; ++j) {
+            V out;
+            if constexpr (VN == 4) {
+                out.x = scalar(j, inv.x); out.y = scalar(j, inv.y); out.z = scalar(j, inv.z); out.w = scalar(j, inv.w);
+            } else {
+                out.x = scalar(j, inv.x); out.y = scalar(j, inv.y);
+            }
+            st_stream(reinterpret_cast<V*>(static_cast<T*>(args.y[j]) + head) + v, out);
+        }
+    }
+    for (int j = 0; j < m; ++j) {
+        T* y = static_cast<T*>(args.y[j]);
+        for (long long k = gtid; k < head; k += gstride) y[k] = scalar(j, x[k]);
+        for (long long k = head + nvec * VN + gtid; k < n; k += gstride) y[k] = scalar(j, x[k]);
+    }
+}
+
 // The reference's no-"output" variant (generate.py:284,392-394): reduce y instead of storing it.
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
@@ -690,6 +845,8 @@ struct LaunchCfg {
                                    const T*, T*, long long, long long, long long);                 \
     cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg&, const TableView&,         \
                                   const T*, double*, long long);                                   \
+    cudaError_t launch_multi_##NAME(int order, const LaunchCfg&, const MultiArgs&, const T*,       \
+                                    long long, long long, long long);                              \
     cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* blocks_per_sm);
 AI_DECLARE_UNIT(cheb_f32, float)
 AI_DECLARE_UNIT(cheb_f64, double)

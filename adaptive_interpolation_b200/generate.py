@@ -235,6 +235,35 @@ def run_multi(x, ap, devices=None):
     return seconds, out
 
 
+def run_many(x, approxs):
+    """Several approximations of one dtype over the SAME points in one pass (ai_eval_multi_*; no
+    reference counterpart -- the reference re-reads x once per generated kernel).  Returns
+    (seconds, [y_0, ..]): the timed region is the device work only, as in run_single.  The library
+    fuses the tables into one kernel when they share basis and order and fit in shared memory
+    together, else launches them back to back; the outputs are bit-identical to run() either way."""
+    torch = _backend()
+    approxs = list(approxs)
+    if not 1 <= len(approxs) <= _cabi.MAX_MULTI:
+        raise Exception("run_many takes 1..%d approximations, got %d" % (_cabi.MAX_MULTI, len(approxs)))
+    dev = torch.cuda.current_device()
+    tabs = [device_table(ap, dev) for ap in approxs]
+    dt = tabs[0].flat.dtype
+    if any(t.flat.dtype != dt for t in tabs):
+        raise Exception("run_many needs approximations of one dtype")
+    x_dev, was_numpy = _as_device(torch, x, dt, torch.device("cuda", dev))
+    ys = [torch.empty_like(x_dev) for _ in tabs]
+    stream = torch.cuda.current_stream(x_dev.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    e0.record()
+    tables.DeviceTable.eval_multi_ptr(tabs, x_dev.data_ptr(), [y.data_ptr() for y in ys], x_dev.numel(),
+                                      stream.cuda_stream)
+    e1.record()
+    e1.synchronize()
+    seconds = e0.elapsed_time(e1) * 1e-3
+    return seconds, [y.cpu().numpy() if was_numpy else y for y in ys]
+
+
 def run_index(x, approx):
     """Leaf ordinal per point (bit-exact with the reference's BST walk, approximator.py:285-290)."""
     torch = _backend()

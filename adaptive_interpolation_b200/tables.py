@@ -279,6 +279,21 @@ class DeviceTable(object):
         fn = _cabi.lib().ai_eval_sum_f32 if self.flat.dtype == np.float32 else _cabi.lib().ai_eval_sum_f64
         _cabi.check(fn(self._h, x_ptr, result_ptr, int(n), stream))
 
+    @staticmethod
+    def eval_multi_ptr(tabs, x_ptr, y_ptrs, n, stream=None):
+        """Several tables over the same x in one pass (ai_eval_multi_*).  Returns True when the
+        fused kernel ran, False when the library issued one launch per table."""
+        m = len(tabs)
+        if m != len(y_ptrs):
+            raise ValueError("one output pointer per table")
+        f32 = tabs[0].flat.dtype == np.float32
+        fn = _cabi.lib().ai_eval_multi_f32 if f32 else _cabi.lib().ai_eval_multi_f64
+        hs = (ctypes.c_void_p * m)(*[t._h for t in tabs])
+        ys = (ctypes.c_void_p * m)(*[int(p) for p in y_ptrs])
+        fused = ctypes.c_int(0)
+        _cabi.check(fn(hs, m, x_ptr, ys, int(n), stream, ctypes.byref(fused)))
+        return bool(fused.value)
+
     def eval_host(self, x, y=None):
         """The reference-facing call on HOST arrays: H2D + kernel + D2H pipelined inside the
         library (ai_eval_host_*).  Returns (y, kernel_ms)."""

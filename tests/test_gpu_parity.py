@@ -641,3 +641,94 @@ def test_full_size_properties(name, log2n):
     br = to_dev(f.breaks)
     li = idx.long()
     assert bool((xs_sorted >= br[li]).all()) and bool((xs_sorted < br[li + 1]).all())
+
+
+# ------------------------------------------------------------------ several tables, one pass
+MULTI_GROUPS = [
+    # (tables, fused?)  -- fused needs one basis / order and packed (<= 32 / 16 leaves) tables
+    (["approx__32o6-p1.19209289551e-06", "approximations__32o6-p1.19209289551e-06"], True),
+    (["approx__32o6-p1.19209289551e-06", "approximations__32o6-p1.19209289551e-06",
+      "approx__ci32o6-p1.19209289551e-06", "approx__32o6-p1.19209289551e-06"], True),
+    (["approx__64o6-p1.19209289551e-06", "approximations__64o6-p1.19209289551e-06",
+      "approx__ci64o6-p1.19209289551e-06"], True),
+    (["gen__cfg3_j0_cheb_o13_f64", "approx__64o13-p1.19209289551e-06"], True),       # 8 leaves + select-mode table
+    (["approx__32o13-p1.19209289551e-06", "approx__ci32o13-p1.19209289551e-06"], True),
+    (["gen__j0_leg_o7_f32", "gen__cfg4_f1_leg_o7_f32"], False),                      # 99 leaves: bank mode
+    (["approx__32o6-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06"], False),  # orders differ
+    (["gen__j0_mono_o5_f64", "gen__j0_mono_o5_f64"], True),
+    (["approx__64o3-p1.19209289551e-06"], False),                                    # m = 1
+]
+
+
+@pytest.mark.parametrize("names,fused", MULTI_GROUPS)
+@pytest.mark.parametrize("n,offset", [(0, 0), (1, 0), (5, 0), (4099, 0), (4099, 3), ((1 << 20) + 77, 1), (1 << 22, 0)])
+def test_multi_table_outputs_equal_single_table_outputs(names, fused, n, offset):
+    """ai_eval_multi_* == ai_eval_* per table, bit for bit, on both of its paths; x offset by a
+    few elements exercises the scalar head / tail and the aligned-together requirement."""
+    tabs = [dev_table(nm) for nm in names]
+    dt = tabs[0].flat.dtype
+    lb = min(float(t.flat.breaks[0]) for t in tabs)
+    ub = max(float(t.flat.breaks[-1]) for t in tabs)
+    rng = np.random.default_rng(n + offset)
+    x = rng.uniform(lb - 0.5, ub + 0.5, n + offset).astype(dt)
+    if n >= 5:
+        x[offset:offset + 4] = [np.nan, np.inf, -np.inf, lb]
+    xd = to_dev(x)[offset:]
+    s = torch.cuda.current_stream().cuda_stream
+    ys = [torch.full((n + offset,), 7.0, dtype=xd.dtype, device="cuda")[offset:] for _ in tabs]
+    ran_fused = tables.DeviceTable.eval_multi_ptr(tabs, xd.data_ptr(), [y.data_ptr() for y in ys], n, s)
+    torch.cuda.synchronize()
+    assert ran_fused == (fused and n > 0)
+    for t, y in zip(tabs, ys):
+        want = torch.empty_like(xd)
+        t.eval_ptr(xd.data_ptr(), want.data_ptr(), n, s)
+        torch.cuda.synchronize()
+        assert np.array_equal(y.cpu().numpy(), want.cpu().numpy(), equal_nan=True)
+
+
+def test_multi_table_misaligned_outputs_fall_back():
+    """An output that cannot be 16-byte aligned together with x takes the per-table path."""
+    names = ["approx__32o6-p1.19209289551e-06", "approximations__32o6-p1.19209289551e-06"]
+    tabs = [dev_table(nm) for nm in names]
+    n = 10007
+    x = np.random.default_rng(3).uniform(0, 20, n).astype(np.float32)
+    xd = to_dev(x)
+    y0 = torch.empty(n, dtype=torch.float32, device="cuda")
+    y1 = torch.empty(n + 1, dtype=torch.float32, device="cuda")[1:]
+    s = torch.cuda.current_stream().cuda_stream
+    assert not tables.DeviceTable.eval_multi_ptr(tabs, xd.data_ptr(), [y0.data_ptr(), y1.data_ptr()], n, s)
+    torch.cuda.synchronize()
+    assert np.array_equal(y0.cpu().numpy(), gpu_eval(tabs[0], x))
+    assert np.array_equal(y1.cpu().numpy(), gpu_eval(tabs[1], x))
+
+
+def test_multi_table_argument_errors():
+    L = _cabi.lib()
+    t32, t64 = dev_table("approx__32o6-p1.19209289551e-06"), dev_table("approx__64o6-p1.19209289551e-06")
+    xd = torch.zeros(64, dtype=torch.float32, device="cuda")
+    y = torch.zeros(64, dtype=torch.float32, device="cuda")
+    y2 = torch.zeros(64, dtype=torch.float32, device="cuda")
+    hs = (ctypes.c_void_p * 2)(t32.handle, t64.handle)
+    ys = (ctypes.c_void_p * 2)(y.data_ptr(), y2.data_ptr())
+    assert L.ai_eval_multi_f32(hs, 2, xd.data_ptr(), ys, 64, None, None) == 5          # AI_ERR_DTYPE
+    hs = (ctypes.c_void_p * 2)(t32.handle, t32.handle)
+    same = (ctypes.c_void_p * 2)(y.data_ptr(), y.data_ptr())
+    assert L.ai_eval_multi_f32(hs, 2, xd.data_ptr(), same, 64, None, None) == 1        # same output twice
+    assert b"same buffer" in L.ai_last_error()
+    assert L.ai_eval_multi_f32(hs, 5, xd.data_ptr(), ys, 64, None, None) == 1          # m > AI_MAX_MULTI
+    assert L.ai_eval_multi_f32(hs, 0, xd.data_ptr(), ys, 64, None, None) == 1
+    assert L.ai_eval_multi_f32(None, 2, xd.data_ptr(), ys, 64, None, None) == 1
+    assert L.ai_eval_multi_f32(hs, 2, xd.data_ptr(), ys, -1, None, None) == 1
+
+
+def test_run_many_matches_run():
+    aps = [golden("approx__32o6-p1.19209289551e-06"), golden("approximations__32o6-p1.19209289551e-06")]
+    x = np.random.default_rng(5).uniform(0, 20, 100003).astype(np.float32)
+    seconds, ys = generate.run_many(x, aps)
+    assert seconds > 0 and len(ys) == 2
+    for ap, y in zip(aps, ys):
+        assert np.array_equal(y, generate.run(x, ap))
+    with pytest.raises(Exception):
+        generate.run_many(x, [])
+    with pytest.raises(Exception):
+        generate.run_many(x, [aps[0], golden("approx__64o6-p1.19209289551e-06")])
