@@ -73,6 +73,12 @@ struct DeviceGuard {
 
 constexpr int kGridMaxExact = 16384;   // cells allowed when the grid alone resolves the leaf
 constexpr int kGridMaxSearch = 4096;   // cells when a search follows anyway
+// Tables far beyond shared memory (the reference's missing order-3 / 2.2e-14 fits have 1e4-1e5
+// leaves, .MISSING_LARGE_BLOBS) read everything through L2 anyway: there the grid may grow with
+// the table (one L2 access instead of a long search), up to 4 MiB of 32-bit entries.
+constexpr int64_t kLargeTableLeaves = 4096;
+constexpr int64_t kGridMaxLarge = 1 << 20;
+constexpr int64_t kMaxLeaves = 1 << 24;
 
 // Test hook: AI_B200_MAX_CELLS=<n> caps both budgets, forcing the search path on tables whose
 // breakpoints would otherwise sit on cell edges (tests/test_gpu_parity.py).
@@ -127,7 +133,7 @@ namespace {
 struct GridPlan {
     int p = 0, K = 0, G = 0;
     long long g0 = 0;
-    std::vector<uint16_t> first;
+    std::vector<uint32_t> first;
     // rank mode (see Lookup::rank_guess): coarse cell = fine cell / q, leaf = rank in cont
     int rank_mode = 0;
     unsigned div_mul = 0, div_shift = 0, div_add = 0;
@@ -209,14 +215,19 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
     long long g0 = 0, gl = 0;
     int p = 0;
     bool exact = false;
-    if (p_exact >= 0 && fits(p_exact, grid_budget(kGridMaxExact), &g0, &gl)) {
+    int budget_exact = kGridMaxExact, budget_search = kGridMaxSearch;
+    if (L > kLargeTableLeaves) {
+        budget_exact = (int)std::min<int64_t>(kGridMaxLarge, std::max<int64_t>(kGridMaxExact, 4 * L));
+        budget_search = (int)std::min<int64_t>(kGridMaxLarge, 4 * L);
+    }
+    if (p_exact >= 0 && fits(p_exact, grid_budget(budget_exact), &g0, &gl)) {
         p = p_exact;
         exact = true;
     } else {
         // finest grid within the budget; p may be negative for very wide domains
         bool found = false;
         for (int q = 60; q >= -1000; --q) {
-            if (fits(q, grid_budget(kGridMaxSearch), &g0, &gl)) { p = q; found = true; break; }
+            if (fits(q, grid_budget(budget_search), &g0, &gl)) { p = q; found = true; break; }
         }
         if (!found) return fail(AI_ERR_TABLE, "cannot build a lookup grid for domain [%g, %g]", b.front(), b.back());
     }
@@ -238,7 +249,7 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
         l = std::min<int64_t>(std::max<int64_t>(l, 0), L - 1);
         if (g == G - 1) l = L - 1;
         if (g == 0) f = 0;
-        out->first[g] = (uint16_t)f;
+        out->first[g] = (uint32_t)f;
         maxspan = std::max(maxspan, l - f);
     }
     int K = 0;
@@ -259,15 +270,18 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     const int hdr = (t->basis == ai::kMono) ? 0 : 2;
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
-    const int fshift = (L <= 256) ? 2 : 1;               // 8-bit entries when they fit, else 16-bit
-    const int off_breaks = round_up16((size_t)gp.G * (fshift == 2 ? 1 : 2));
+    const int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
+    const int off_breaks = round_up16((size_t)gp.G * (size_t)(4 >> fshift));
     const int off_records = off_breaks + round_up16((size_t)(L + 1 + pad) * sizeof(T));
     const size_t total = (size_t)off_records + (size_t)round_up16((size_t)L * R * sizeof(T));
     image->assign(total, 0);
     if (fshift == 2) {
         for (int g = 0; g < gp.G; ++g) (*image)[off_first + g] = (unsigned char)gp.first[g];
+    } else if (fshift == 1) {
+        uint16_t* f16 = reinterpret_cast<uint16_t*>(image->data() + off_first);
+        for (int g = 0; g < gp.G; ++g) f16[g] = (uint16_t)gp.first[g];
     } else {
-        std::memcpy(image->data() + off_first, gp.first.data(), gp.first.size() * sizeof(uint16_t));
+        std::memcpy(image->data() + off_first, gp.first.data(), gp.first.size() * sizeof(uint32_t));
     }
     t->view.first_shift = fshift;
     T* br = reinterpret_cast<T*>(image->data() + off_breaks);
@@ -317,7 +331,9 @@ int finish_table(ai_table* t) {
         if (!(t->breaks[k] < t->breaks[k + 1]))
             return fail(AI_ERR_TABLE, "breakpoints not strictly increasing at %lld (%.17g, %.17g)",
                         (long long)k, t->breaks[k], t->breaks[k + 1]);
-    if (L > 65535) return fail(AI_ERR_UNSUPPORTED, "more than 65535 leaves (%lld) not supported yet", (long long)L);
+    if (L > kMaxLeaves) return fail(AI_ERR_UNSUPPORTED, "more than %lld leaves (%lld) not supported", (long long)kMaxLeaves, (long long)L);
+    if ((int64_t)L * (t->order + 4) * 8 > (int64_t)1 << 30)
+        return fail(AI_ERR_UNSUPPORTED, "table image would exceed 1 GiB (%lld leaves, order %d)", (long long)L, t->order);
 
     GridPlan gp;
     int rc = plan_grid(t->breaks, t->dtype, &gp);

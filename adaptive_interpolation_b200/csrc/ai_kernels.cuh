@@ -100,7 +100,7 @@ struct TableView {
     int soff_breaks, soff_records; // bank modes: byte offsets of the replicated sections in shared memory
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
-    int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit
+    int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit, 0 -> 32-bit
     int rank_mode;                 // 1: leaf = rank in cont_mask of the coarse cell (no table read)
     unsigned div_mul, div_shift;   // coarse cell = (fine cell * div_mul) >> div_shift  (exact / q)
     unsigned div_add;              // -g0 * div_mul (mod 2^32): folds the "- g0" into the multiply
@@ -220,9 +220,12 @@ template <typename T> struct Lookup {
         if (fshift == 2) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = table_guess<unsigned char>(cell(x[e]));
-        } else {
+        } else if (fshift == 1) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = table_guess<unsigned short>(cell(x[e]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < N; ++e) i[e] = table_guess<unsigned int>(cell(x[e]));
         }
         if (kstep) {
             // Tables whose breakpoints are off the grid: branch-free forward binary search over

@@ -190,11 +190,10 @@ def _synthetic_table(n_leaves, lo, hi, order, dtype, seed):
     The check is against the oracle restatement, not against frozen reference outputs."""
     from numpy.polynomial import chebyshev as C
     breaks = np.linspace(lo, hi, n_leaves + 1).astype(dtype)
-    coef = np.empty((n_leaves, order + 1), dtype=dtype)
     nodes = np.cos(np.pi * (np.arange(order + 1) + 0.5) / (order + 1))
-    for i in range(n_leaves):
-        a, b = float(breaks[i]), float(breaks[i + 1])
-        coef[i] = C.chebfit(nodes, np.sin(3 * (a + (nodes + 1) * (b - a) / 2)), order)
+    a, b = breaks[:-1].astype(np.float64), breaks[1:].astype(np.float64)
+    vals = np.sin(3 * (a[None, :] + (nodes[:, None] + 1) * (b - a)[None, :] / 2))      # (order+1, L)
+    coef = np.ascontiguousarray(C.chebfit(nodes, vals, order).T).astype(dtype)          # one fit per column
     return tables.FlatTable("chebyshev", order, dtype, breaks, coef)
 
 
@@ -202,6 +201,8 @@ def _synthetic_table(n_leaves, lo, hi, order, dtype, seed):
     (16384, 0.0, 16.0, np.float64, True),       # dyadic: exact grid, 16-bit entries, 2.3 MB of records
     (20000, 0.0, 10.0, np.float64, False),      # non-dyadic widths: grid + search through L2
     (40000, -3.0, 7.0, np.float32, False),
+    (131072, 0.0, 16.0, np.float64, True),      # > 65536 leaves: 32-bit grid entries, exact 131072-cell grid in L2
+    (100000, 0.0, 16.0, np.float64, False),     # the size of the reference's missing order-3 / 2.2e-15 fits
 ])
 def test_large_table_takes_the_global_path(n_leaves, lo, hi, dtype, expect_k0):
     f = _synthetic_table(n_leaves, lo, hi, 3, dtype, 0)
