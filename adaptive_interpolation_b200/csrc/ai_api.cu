@@ -119,6 +119,7 @@ struct ai_table {
     int rank_mode = 0;
     int mode = ai::kSmem;              // table residency: kSmem / kSmemBank / kGlobal / kSmemBankN
     int copies = 1;                    // bank modes: copies per element
+    int packed = 0;                    // 1: records carry the one-element header (modes kSmemP / kSmemBankP)
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
@@ -262,12 +263,79 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
 
 int round_up16(size_t v) { return (int)((v + 15) & ~(size_t)15); }
 
+// The one-element record header of modes kSmemP / kSmemBankP (see ai_kernels.cuh): possible when,
+// for EVERY leaf, a_i has 9 (fp32) / 32 (fp64) trailing zero bits and 2/(b_i-a_i) differs from
+// S0 = max_i 2/(b_i-a_i) only by j_i <= 255 in the exponent field.  Checked on the exact values
+// the unpacked records would hold, so unpacking reproduces them bit for bit.
+template <typename T> struct HeaderPack {
+    bool ok = false;
+    unsigned s0_hi = 0, s0_lo = 0;
+    std::vector<T> word;               // per leaf: (bits of a) | j
+};
+
 template <typename T>
-int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector<unsigned char>* image) {
+HeaderPack<T> plan_header_pack(const ai_table* t) {
+    HeaderPack<T> hp;
+    if (t->basis == ai::kMono || std::getenv("AI_B200_NO_PACKED_HDR")) return hp;
+    const int64_t L = t->L;
+    std::vector<T> a(L), s(L);
+    T smax = 0;
+    for (int64_t i = 0; i < L; ++i) {
+        a[i] = (T)t->breaks[i];
+        const T b = (T)t->breaks[i + 1];
+        s[i] = (T)2 / (b - a[i]);
+        if (!(s[i] > 0) || !std::isfinite(s[i])) return hp;
+        smax = std::max(smax, s[i]);
+    }
+    hp.word.resize(L);
+    if constexpr (sizeof(T) == 4) {
+        uint32_t s0;
+        std::memcpy(&s0, &smax, 4);
+        for (int64_t i = 0; i < L; ++i) {
+            uint32_t ab, sb;
+            std::memcpy(&ab, &a[i], 4);
+            std::memcpy(&sb, &s[i], 4);
+            const uint32_t d = s0 - sb;
+            if ((ab & 0x1FFu) || (d & 0x7FFFFFu) || (d >> 23) > 255u || (sb >> 23) == 0u) return hp;
+            const uint32_t w = ab | (d >> 23);
+            // the device formula, checked here on the host
+            const uint32_t ua = w & 0xFFFFFE00u, us = w * 0xFF800000u + s0;
+            if (ua != ab || us != sb) return hp;
+            std::memcpy(&hp.word[i], &w, 4);
+        }
+        hp.s0_hi = s0;
+    } else {
+        uint64_t s0;
+        std::memcpy(&s0, &smax, 8);
+        for (int64_t i = 0; i < L; ++i) {
+            uint64_t ab, sb;
+            std::memcpy(&ab, &a[i], 8);
+            std::memcpy(&sb, &s[i], 8);
+            const uint64_t d = s0 - sb;
+            if ((ab & 0xFFFFFFFFull) || (d & ((1ull << 52) - 1)) || (d >> 52) > 255ull || ((sb >> 52) & 0x7FF) == 0) return hp;
+            const uint64_t w = ab | (d >> 52);
+            const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
+            const uint64_t ua = (uint64_t)hi << 32;
+            const uint64_t us = ((uint64_t)((uint32_t)(s0 >> 32) - (lo << 20)) << 32) | (uint32_t)s0;
+            if (ua != ab || us != sb) return hp;
+            std::memcpy(&hp.word[i], &w, 8);
+        }
+        hp.s0_hi = (uint32_t)(s0 >> 32);
+        hp.s0_lo = (uint32_t)s0;
+    }
+    hp.ok = true;
+    return hp;
+}
+
+template <typename T>
+int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector<unsigned char>* image,
+                const HeaderPack<T>* pack = nullptr) {
     const int n = t->order;
     const int64_t L = t->L;
-    const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T)) : ai::rec_stride(t->basis, n);
-    const int hdr = (t->basis == ai::kMono) ? 0 : 2;
+    const bool packed = pack && pack->ok && !global_layout;
+    const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T))
+                                : (packed ? ai::rec_stride_packed(n) : ai::rec_stride(t->basis, n));
+    const int hdr = (t->basis == ai::kMono) ? 0 : (packed ? 1 : 2);
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
     const int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
@@ -290,14 +358,19 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     T* rec = reinterpret_cast<T*>(image->data() + off_records);
     for (int64_t i = 0; i < L; ++i) {
         T* r = rec + i * R;
-        if (hdr) {
+        if (hdr == 2) {
             const T a = (T)t->breaks[i], b = (T)t->breaks[i + 1];
             r[0] = a;
             r[1] = (T)2 / (b - a);       // in T arithmetic: generate.py:83 `(2./(b - a))`
+        } else if (hdr == 1) {
+            r[0] = pack->word[i];
         }
         for (int j = 0; j <= n; ++j) r[hdr + j] = (T)t->coef[i * (n + 1) + j];
     }
     t->rstride = R;
+    t->packed = packed ? 1 : 0;
+    t->view.s0_hi = packed ? pack->s0_hi : 0;
+    t->view.s0_lo = packed ? pack->s0_lo : 0;
     t->view.image_bytes = (int)total;
     t->view.n_records_elems = (int)(L * R);
     t->view.n_breaks_elems = (int)(L + 1 + pad);
@@ -405,13 +478,27 @@ int finish_table(ai_table* t) {
                     ? (double)reinterpret_cast<const float*>(rec)[k] : reinterpret_cast<const double*>(rec)[k];
         }
     }
+    // one-element record header where the table allows it (bit-identical values, one shared-memory
+    // wavefront less per 32 points; two less in fp64)
+    if (mode == ai::kSmem || mode == ai::kSmemBank) {
+        bool packed = false;
+        if (t->dtype == AI_DTYPE_F32) {
+            const HeaderPack<float> hp = plan_header_pack<float>(t);
+            if (hp.ok) { rc = build_image<float>(t, gp, false, &image, &hp); packed = true; }
+        } else {
+            const HeaderPack<double> hp = plan_header_pack<double>(t);
+            if (hp.ok) { rc = build_image<double>(t, gp, false, &image, &hp); packed = true; }
+        }
+        if (rc) return rc;
+        if (packed) mode = (mode == ai::kSmem) ? ai::kSmemP : ai::kSmemBankP;
+    }
     t->mode = mode;
     t->copies = copies;
     t->view.copies = copies;
     t->smem_resident = (mode != ai::kGlobal);
     t->eval_smem = 0;
-    if (mode == ai::kSmem) t->eval_smem = t->view.image_bytes;
-    if (mode == ai::kSmemBank || mode == ai::kSmemBankN)
+    if (mode == ai::kSmem || mode == ai::kSmemP) t->eval_smem = t->view.image_bytes;
+    if (ai::mode_bank(mode))
         t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
     t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
     AI_CUDA(cudaMalloc(&t->d_image, image.size()));
@@ -440,7 +527,7 @@ int finish_table(ai_table* t) {
     if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->eval_smem);
     if (t->mode != ai::kGlobal && t->aux_smem > 48 * 1024) {
         int dummy = 0;      // opt the reduction kernel (packed layout) into large shared memory too
-        rc = prepare_dispatch(t->basis, t->dtype, t->order, ai::kSmem, t->aux_smem, &dummy);
+        rc = prepare_dispatch(t->basis, t->dtype, t->order, t->packed ? ai::kSmemP : ai::kSmem, t->aux_smem, &dummy);
         if (rc) return rc;
     }
     t->blocks_per_sm = bps;
@@ -543,7 +630,8 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     ai::MultiArgs args{};
     for (int j = 0; j < m && fuse; ++j) {
         const ai_table* t = tabs[j];
-        fuse = t->basis == t0->basis && t->order == t0->order && (t->mode == ai::kSmem || t->mode == ai::kSelect)
+        fuse = t->basis == t0->basis && t->order == t0->order && t->packed == t0->packed
+               && (t->mode == ai::kSmem || t->mode == ai::kSmemP || t->mode == ai::kSelect)
                && (reinterpret_cast<uintptr_t>(y[j]) % 16) == (ax % 16);
         args.tv[j] = t->view;
         args.y[j] = y[j];
@@ -572,13 +660,13 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     cfg.select = nullptr;
     cudaError_t e;
     if constexpr (sizeof(T) == 4) {
-        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f32(t0->order, cfg, args, x, n, head, nvec);
-        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f32(t0->order, cfg, args, x, n, head, nvec);
-        else e = ai::launch_multi_mono_f32(t0->order, cfg, args, x, n, head, nvec);
+        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f32(t0->order, t0->packed, cfg, args, x, n, head, nvec);
+        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f32(t0->order, t0->packed, cfg, args, x, n, head, nvec);
+        else e = ai::launch_multi_mono_f32(t0->order, t0->packed, cfg, args, x, n, head, nvec);
     } else {
-        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f64(t0->order, cfg, args, x, n, head, nvec);
-        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f64(t0->order, cfg, args, x, n, head, nvec);
-        else e = ai::launch_multi_mono_f64(t0->order, cfg, args, x, n, head, nvec);
+        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f64(t0->order, t0->packed, cfg, args, x, n, head, nvec);
+        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f64(t0->order, t0->packed, cfg, args, x, n, head, nvec);
+        else e = ai::launch_multi_mono_f64(t0->order, t0->packed, cfg, args, x, n, head, nvec);
     }
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "multi-table kernel launch failed: %s", cudaGetErrorString(e));
     if (fused_out) *fused_out = 1;
@@ -625,7 +713,7 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     cfg.stream = s;
     cfg.select = nullptr;
     cudaError_t e;
-    const int m = (t->mode == ai::kGlobal) ? ai::kGlobal : ai::kSmem;
+    const int m = (t->mode == ai::kGlobal) ? ai::kGlobal : (t->packed ? ai::kSmemP : ai::kSmem);
     if constexpr (sizeof(T) == 4) {
         if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, m, cfg, t->view, x, result, n);
         else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, m, cfg, t->view, x, result, n);
@@ -899,7 +987,8 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->record_stride = t->rstride;
     info->image_bytes = t->view.image_bytes;
     info->smem_bytes = t->eval_smem;
-    info->residency = t->mode;
+    info->residency = (t->mode == ai::kSmemP) ? ai::kSmem : (t->mode == ai::kSmemBankP ? ai::kSmemBank : t->mode);
+    info->header_packed = t->packed;
     info->bank_copies = t->copies;
     info->smem_resident = t->smem_resident;
     info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : 0);

@@ -26,7 +26,7 @@ struct Unit {
         return cudaGetLastError();
     }
     static cudaError_t sum(const LaunchCfg& c, const TableView& tv, const T* x, double* r, long long n) {
-        if constexpr (MODE == kSmemBank || MODE == kSmemBankN || MODE == kSelect) {
+        if constexpr (mode_bank(MODE) || MODE == kSelect) {
             return cudaErrorInvalidValue;
         } else {
             eval_sum_kernel<BASIS, ORDER, T, MODE><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(tv, x, r, n);
@@ -35,12 +35,13 @@ struct Unit {
     }
     static cudaError_t multi(const LaunchCfg& c, const MultiArgs& a, const T* x, long long n, long long head,
                              long long nvec) {
+        constexpr bool PK = mode_packed_hdr(MODE);
         if (c.smem_bytes > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(eval_multi_kernel<BASIS, ORDER, T>,
+            cudaError_t e = cudaFuncSetAttribute(eval_multi_kernel<BASIS, ORDER, T, PK>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
             if (e != cudaSuccess) return e;
         }
-        eval_multi_kernel<BASIS, ORDER, T><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(a, x, n, head, nvec);
+        eval_multi_kernel<BASIS, ORDER, T, PK><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(a, x, n, head, nvec);
         return cudaGetLastError();
     }
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
@@ -49,7 +50,7 @@ struct Unit {
             e = cudaFuncSetAttribute(eval_kernel<BASIS, ORDER, T, MODE>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
             if (e != cudaSuccess) return e;
-            if constexpr (MODE == kSmem || MODE == kGlobal) {
+            if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kGlobal) {
                 e = cudaFuncSetAttribute(eval_sum_kernel<BASIS, ORDER, T, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
                 if (e != cudaSuccess) return e;
@@ -70,6 +71,10 @@ struct Switch {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::eval(a...);
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::eval(a...);
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::eval(a...);
+            if constexpr (BASIS != kMono) {          // the monomial record has no header to pack
+                if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::eval(a...);
+                if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::eval(a...);
+            }
             return cudaErrorInvalidValue;
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::eval(order, mode, a...);
@@ -78,14 +83,22 @@ struct Switch {
     template <typename... A> static cudaError_t sum(int order, int mode, A&&... a) {
         if (order == ORDER) {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::sum(a...);
+            if constexpr (BASIS != kMono) {
+                if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::sum(a...);
+            }
             return Unit<BASIS, T, ORDER, kSmem>::sum(a...);
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::sum(order, mode, a...);
         else return cudaErrorInvalidValue;
     }
-    template <typename... A> static cudaError_t multi(int order, A&&... a) {
-        if (order == ORDER) return Unit<BASIS, T, ORDER, kSmem>::multi(a...);
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::multi(order, a...);
+    template <typename... A> static cudaError_t multi(int order, int packed, A&&... a) {
+        if (order == ORDER) {
+            if constexpr (BASIS != kMono) {
+                if (packed) return Unit<BASIS, T, ORDER, kSmemP>::multi(a...);
+            }
+            return packed ? cudaErrorInvalidValue : Unit<BASIS, T, ORDER, kSmem>::multi(a...);
+        }
+        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::multi(order, packed, a...);
         else return cudaErrorInvalidValue;
     }
     static cudaError_t prepare(int order, int mode, int smem_bytes, int* bps) {
@@ -95,6 +108,10 @@ struct Switch {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::prepare(smem_bytes, bps);
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::prepare(smem_bytes, bps);
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::prepare(smem_bytes, bps);
+            if constexpr (BASIS != kMono) {
+                if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::prepare(smem_bytes, bps);
+                if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::prepare(smem_bytes, bps);
+            }
             return cudaErrorInvalidValue;
         }
         if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::prepare(order, mode, smem_bytes, bps);
@@ -115,9 +132,9 @@ struct Switch {
                                   const T* x, double* r, long long n) {                           \
         return Switch<BASIS, T>::sum(order, mode, c, tv, x, r, n);                                \
     }                                                                                             \
-    cudaError_t launch_multi_##NAME(int order, const LaunchCfg& c, const MultiArgs& a, const T* x, \
-                                    long long n, long long head, long long nvec) {                \
-        return Switch<BASIS, T>::multi(order, c, a, x, n, head, nvec);                            \
+    cudaError_t launch_multi_##NAME(int order, int packed, const LaunchCfg& c, const MultiArgs& a, \
+                                    const T* x, long long n, long long head, long long nvec) {    \
+        return Switch<BASIS, T>::multi(order, packed, c, a, x, n, head, nvec);                    \
     }                                                                                             \
     cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* bps) {                   \
         return Switch<BASIS, T>::prepare(order, mode, smem_bytes, bps);                           \

@@ -74,7 +74,16 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              (tools/micro/shfl_bench.cu: LDS and SHFL share that path, LDC does not but
 //              serialises per distinct address).
 // In both bank modes the breakpoint array read by the search is replicated the same way.
-enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4 };
+//   kSmemP / kSmemBankP  as kSmem / kSmemBank with a ONE-element record header: dyadic tables (every
+//              table the reference's bisection builds on a domain with few significant bits) have
+//              a_i with >= 9 (fp32) / 32 (fp64) trailing zero mantissa bits and 2/(b_i-a_i) =
+//              S0 * 2^-j_i exactly, so [a, 2/(b-a)] packs into one word (a's bits | j) that two
+//              integer instructions unpack.  One shared-memory wavefront less per 32 points on the
+//              return path that bounds random points (fp64: two less); the unpacked values are
+//              the stored ones bit for bit (verified per leaf on the host, else not packed).
+enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4, kSmemP = 5, kSmemBankP = 6 };
+__host__ __device__ constexpr bool mode_packed_hdr(int mode) { return mode == kSmemP || mode == kSmemBankP; }
+__host__ __device__ constexpr bool mode_bank(int mode) { return mode == kSmemBank || mode == kSmemBankN || mode == kSmemBankP; }
 constexpr int kMaxRecord = 16 + 1 + 2;         // AI_MAX_ORDER + 1 coefficients + [a, 2/(b-a)]
 // kSelect's table, passed by value as a kernel parameter; empty in every other mode
 template <typename T, int MODE> struct SelectTable {};
@@ -83,7 +92,7 @@ template <typename T> struct SelectTable<T, kSelect> {
     T rec[2][kMaxRecord];           // [a, 2/(b-a), c0..cn] ([c0..cn] for the monomial basis)
 };
 template <typename T, int MODE> struct Copies {
-    static constexpr int value = (MODE == kSmemBank) ? (sizeof(T) == 4 ? 32 : 16) : 1;
+    static constexpr int value = (MODE == kSmemBank || MODE == kSmemBankP) ? (sizeof(T) == 4 ? 32 : 16) : 1;
 };
 
 // Everything a kernel needs to know about a table; passed by value (kernel parameter space).
@@ -108,6 +117,7 @@ struct TableView {
     double scale;                  // 2^p (exact in T)
     double lo, hi;                 // g0 and g0+G-1 as floating point (exact in T)
     double inv_order;              // T(1./n) widened: the Legendre-like recurrence's divisor
+    unsigned s0_hi, s0_lo;         // packed header: bits of S0 = max_i 2/(b_i-a_i) (fp32: s0_hi only)
 };
 
 // ---------------------------------------------------------------------------------- helpers
@@ -126,9 +136,12 @@ __host__ __device__ constexpr int rec_stride_global(int basis, int order, int el
     const int per = 16 / elem_bytes;
     return (order + 1 + (basis == kMono ? 0 : 2) + per - 1) / per * per;
 }
+// packed header (kSmemP / kSmemBankP): [a|j, c0..cn]
+__host__ __device__ constexpr int rec_stride_packed(int order) { return ((order + 2) | 1); }
 template <int BASIS, int ORDER, typename T, int MODE>
 __host__ __device__ constexpr int rec_stride_for() {
-    return MODE == kGlobal ? rec_stride_global(BASIS, ORDER, (int)sizeof(T)) : rec_stride(BASIS, ORDER);
+    return MODE == kGlobal ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
+                           : (mode_packed_hdr(MODE) ? rec_stride_packed(ORDER) : rec_stride(BASIS, ORDER));
 }
 
 __device__ __forceinline__ float  fma_(float a, float b, float c)    { return __fmaf_rn(a, b, c); }
@@ -274,6 +287,26 @@ template <int BASIS, int ORDER, typename T> struct Record {
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = rec[k * STRIDE];
     }
+    // packed header: rec = [w, c0..cn] with w = (bits of a) | j and 2/(b-a) = S0 * 2^-j.
+    // fp32: a = w & ~0x1ff, bits(2/(b-a)) = bits(S0) - (j << 23) (one IMAD: the multiply by
+    // -2^23 keeps only w's low 9 bits).  fp64: high word = a's high word (its low word is 0),
+    // low word = j, bits(2/(b-a)) = bits(S0) - (j << 52).
+    template <int STRIDE = 1>
+    __device__ __forceinline__ void load_packed(const T* __restrict__ rec, unsigned s0_hi, unsigned s0_lo) {
+        static_assert(HDR == 2, "the monomial basis has no header");
+        const T w = rec[0];
+#pragma unroll
+        for (int k = 0; k <= ORDER; ++k) v[2 + k] = rec[(1 + k) * STRIDE];
+        if constexpr (sizeof(T) == 4) {
+            const unsigned u = __float_as_uint(w);
+            v[0] = __uint_as_float(u & 0xFFFFFE00u);
+            v[1] = __uint_as_float(u * 0xFF800000u + s0_hi);
+        } else {
+            const int hi = __double2hiint(w), lo = __double2loint(w);
+            v[0] = __hiloint2double(hi, 0);
+            v[1] = __hiloint2double((int)(s0_hi - ((unsigned)lo << 20)), (int)s0_lo);
+        }
+    }
     __device__ __forceinline__ void load_strided(const T* __restrict__ rec, int stride) {
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = rec[k * stride];
@@ -405,10 +438,12 @@ __device__ __forceinline__ float2 eval_record_pair(const Record<BASIS, ORDER, fl
     return eval_values<BASIS, ORDER, float2>(v, make_float2(xa, xb));
 }
 
-template <int BASIS, int ORDER, typename T, int STRIDE = 1, bool VEC = false>
-__device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order) {
+template <int BASIS, int ORDER, typename T, int STRIDE = 1, bool VEC = false, bool PK = false>
+__device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_order, unsigned s0_hi = 0,
+                                       unsigned s0_lo = 0) {
     Record<BASIS, ORDER, T> r;
     if constexpr (VEC) r.load_vec(rec);
+    else if constexpr (PK) r.template load_packed<STRIDE>(rec, s0_hi, s0_lo);
     else r.template load<STRIDE>(rec);
     return eval_record<BASIS, ORDER, T>(r, x, inv_order);
 }
@@ -424,7 +459,7 @@ template <typename T, int MODE>
 __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
     if constexpr (MODE == kGlobal || MODE == kSelect) {
         return tv.image;
-    } else if constexpr (MODE == kSmem) {
+    } else if constexpr (MODE == kSmem || MODE == kSmemP) {
         const int4* src = reinterpret_cast<const int4*>(tv.image);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int k = threadIdx.x; k < tv.image_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
@@ -435,7 +470,7 @@ __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, 
         const int4* src = reinterpret_cast<const int4*>(tv.image);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int k = threadIdx.x; k < tv.off_breaks / 16; k += blockDim.x) dst[k] = __ldg(src + k);
-        const int cp = (MODE == kSmemBank) ? Copies<T, MODE>::value : tv.copies;
+        const int cp = (MODE == kSmemBankN) ? tv.copies : Copies<T, MODE>::value;
         const int sh = 31 - __clz(cp);
         const T* bsrc = reinterpret_cast<const T*>(tv.image + tv.off_breaks);
         T* bdst = reinterpret_cast<T*>(smem + tv.soff_breaks);
@@ -461,10 +496,11 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
 
     Lookup<T> lk;
     lk.init(tv, base);
-    constexpr bool kBank = (MODE == kSmemBank || MODE == kSmemBankN);
+    constexpr bool kBank = mode_bank(MODE);
     constexpr bool VEC = (MODE == kGlobal);                        // 128-bit record loads
+    constexpr bool PK = mode_packed_hdr(MODE);                     // one-element record header
     // copies per record element: compile-time except in kSmemBankN
-    const int cp = (MODE == kSmemBank) ? Copies<T, MODE>::value : (MODE == kSmemBankN ? tv.copies : 1);
+    const int cp = (MODE == kSmemBankN) ? tv.copies : Copies<T, MODE>::value;
     const int R = rec_stride_for<BASIS, ORDER, T, MODE>() * cp;    // record stride in elements
     // bank-private layout: lane l reads copy l mod cp of every element
     const T* records = reinterpret_cast<const T*>(base + (kBank ? tv.soff_records : tv.off_records))
@@ -480,6 +516,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
         } else {
             const T* p = records + leaf * R;
             if constexpr (VEC) r.load_vec(p);
+            else if constexpr (PK) r.template load_packed<Copies<T, MODE>::value>(p, tv.s0_hi, tv.s0_lo);
             else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);
             else if constexpr (MODE == kSmemBankN) r.load_strided(p, cp);
             else r.template load<1>(p);
@@ -655,7 +692,7 @@ struct MultiArgs {
     int m;
 };
 
-template <int BASIS, int ORDER, typename T>
+template <int BASIS, int ORDER, typename T, bool PK>
 __global__ void __launch_bounds__(kBlock, 1)
 eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ x,
                   long long n, long long head, long long nvec) {
@@ -673,9 +710,13 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
     constexpr int U = UnrollMulti<T>::value;
     constexpr long long kTile = (long long)kBlock * U;
     constexpr int NE = U * VN;
-    constexpr int R = rec_stride(BASIS, ORDER);
+    constexpr int R = PK ? rec_stride_packed(ORDER) : rec_stride(BASIS, ORDER);
     const V* __restrict__ xv = reinterpret_cast<const V*>(x + head);
     const long long full_tiles = nvec / kTile;
+    auto load_rec = [&](Record<BASIS, ORDER, T>& r, const T* p, int j) {
+        if constexpr (PK) r.template load_packed<1>(p, args.tv[j].s0_hi, args.tv[j].s0_lo);
+        else r.template load<1>(p);
+    };
 
     auto load_tile = [&](V (&buf)[U], long long tile) {
         const long long base = tile * kTile + threadIdx.x;
@@ -686,7 +727,9 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
         Lookup<T> lk;
         lk.init(args.tv[j], smem + args.soff[j]);
         const T* records = reinterpret_cast<const T*>(smem + args.soff[j] + args.tv[j].off_records);
-        return eval_leaf<BASIS, ORDER, T>(records + lk.leaf(xs) * R, xs, (T)0);
+        Record<BASIS, ORDER, T> r;
+        load_rec(r, records + lk.leaf(xs) * R, j);
+        return eval_record<BASIS, ORDER, T>(r, xs, (T)0);
     };
 
     long long tile = blockIdx.x;
@@ -719,7 +762,7 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
             T ys[NE];
             if (uniform) {
                 Record<BASIS, ORDER, T> rec;
-                rec.template load<1>(records + li[0] * R);
+                load_rec(rec, records + li[0] * R, j);
                 if constexpr (sizeof(T) == 4 && AI_PACKED_F32) {
 #pragma unroll
                     for (int e = 0; e < NE; e += 2) {
@@ -735,8 +778,8 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 #pragma unroll
                     for (int e = 0; e < NE; e += 2) {
                         Record<BASIS, ORDER, T> ra, rb;
-                        ra.template load<1>(records + li[e] * R);
-                        rb.template load<1>(records + li[e + 1] * R);
+                        load_rec(ra, records + li[e] * R, j);
+                        load_rec(rb, records + li[e + 1] * R, j);
                         const float2 r2 = eval_record_pair<BASIS, ORDER>(ra, rb, xs[e], xs[e + 1]);
                         ys[e] = r2.x; ys[e + 1] = r2.y;
                     }
@@ -744,7 +787,7 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 #pragma unroll
                     for (int e = 0; e < NE; ++e) {
                         Record<BASIS, ORDER, T> rec;
-                        rec.template load<1>(records + li[e] * R);
+                        load_rec(rec, records + li[e] * R, j);
                         ys[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], (T)0);
                     }
                 }
@@ -790,13 +833,14 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
-    static_assert(MODE == kSmem || MODE == kGlobal, "the reduction variant uses the packed layouts only");
+    static_assert(MODE == kSmem || MODE == kSmemP || MODE == kGlobal, "the reduction variant uses the packed layouts only");
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned char* base = table_base<T, MODE>(tv, smem);
     Lookup<T> lk;
     lk.init(tv, base);
     const T* records = reinterpret_cast<const T*>(base + tv.off_records);
     constexpr int R = rec_stride_for<BASIS, ORDER, T, MODE>();
+    constexpr bool PK = mode_packed_hdr(MODE);
     const T inv_order = (T)tv.inv_order;
     double acc = 0.0;
     const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -804,7 +848,7 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
     for (long long k = gtid; k < n; k += gstride) {
         const T xv = __ldcs(x + k);
         const int i = lk.leaf(xv);
-        acc += (double)eval_leaf<BASIS, ORDER, T>(records + i * R, xv, inv_order);
+        acc += (double)eval_leaf<BASIS, ORDER, T, 1, false, PK>(records + i * R, xv, inv_order, tv.s0_hi, tv.s0_lo);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -848,8 +892,8 @@ struct LaunchCfg {
                                    const T*, T*, long long, long long, long long);                 \
     cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg&, const TableView&,         \
                                   const T*, double*, long long);                                   \
-    cudaError_t launch_multi_##NAME(int order, const LaunchCfg&, const MultiArgs&, const T*,       \
-                                    long long, long long, long long);                              \
+    cudaError_t launch_multi_##NAME(int order, int packed, const LaunchCfg&, const MultiArgs&,     \
+                                    const T*, long long, long long, long long);                    \
     cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* blocks_per_sm);
 AI_DECLARE_UNIT(cheb_f32, float)
 AI_DECLARE_UNIT(cheb_f64, double)

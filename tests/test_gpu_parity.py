@@ -184,6 +184,52 @@ def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
     assert np.array_equal(gpu_eval(tab, g.x), want_y, equal_nan=True)
 
 
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
+    """Dyadic tables carry [a, 2/(b-a)] as one word (a's bits | exponent offset); the two integer
+    instructions that unpack it must reproduce the stored header exactly, so values are the same
+    bits as with the two-element header (AI_B200_NO_PACKED_HDR=1), in both shared-memory layouts,
+    for the evaluation, the reduction and the multi-table kernels."""
+    g = golden(name)
+    monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
+    tab_p = dev_table(name)
+    info_p = tab_p.info()
+    if not info_p["header_packed"]:
+        pytest.skip("table does not qualify for the packed header")
+    assert info_p["residency"] in (0, 1)
+    monkeypatch.setenv("AI_B200_NO_PACKED_HDR", "1")
+    tab_u = dev_table(name)
+    info_u = tab_u.info()
+    assert not info_u["header_packed"] and info_u["residency"] == info_p["residency"]
+    assert info_p["record_stride"] <= info_u["record_stride"]
+    lo, hi = float(g.lower_bound), float(g.upper_bound)
+    x = np.concatenate([g.x, np.random.default_rng(9).uniform(lo, hi, 1 << 18).astype(g.dtype)])
+    y_p = gpu_eval(tab_p, x)
+    assert np.array_equal(y_p, gpu_eval(tab_u, x), equal_nan=True)
+    xin = x[np.isfinite(x)]
+    xd = to_dev(xin)
+    s = torch.cuda.current_stream().cuda_stream
+    sums = []
+    for tab in (tab_p, tab_u):
+        r = torch.zeros(1, dtype=torch.float64, device="cuda")
+        tab.sum_ptr(xd.data_ptr(), r.data_ptr(), xd.numel(), s)
+        torch.cuda.synchronize()
+        sums.append(float(r.item()))
+    # same values; only the order of the per-CTA atomic adds differs between two launches
+    assert abs(sums[0] - sums[1]) <= 1e-12 * float(np.sum(np.abs(y_p[np.isfinite(x)].astype(np.float64))))
+
+
+def test_saved_tables_take_the_packed_header():
+    """All 27 saved approximations are dyadic on [0, 20]: every one with more than two leaves
+    qualifies; the deep config-4 trees (breakpoints with > 15 significant bits) do not."""
+    for name in SAVED:
+        info = dev_table(name).info()
+        assert info["header_packed"] == (1 if info["n_leaves"] > 2 and info["residency"] in (0, 1) else 0), (name, info)
+    assert dev_table("gen__cfg3_j0_cheb_o13_f64").info()["header_packed"] == 1
+    assert dev_table("gen__cfg4_f1_leg_o7_f32").info()["header_packed"] == 0
+
+
 def _synthetic_table(n_leaves, lo, hi, order, dtype, seed):
     """A table the reference has no fixture for (its 5 order-3 / 2.2e-14 pickles with ~1e4-1e5
     leaves are listed in .MISSING_LARGE_BLOBS): uniform leaves, Chebyshev fit of sin(3x) per leaf.
