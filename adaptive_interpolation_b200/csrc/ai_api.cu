@@ -480,7 +480,8 @@ int finish_table(ai_table* t) {
     }
     // one-element record header where the table allows it (bit-identical values, one shared-memory
     // wavefront less per 32 points; two less in fp64)
-    if (mode == ai::kSmem || mode == ai::kSmemBank) {
+    // (a kSelect table keeps a packed image too: the reduction and multi-table kernels read it)
+    if (mode == ai::kSmem || mode == ai::kSmemBank || mode == ai::kSelect) {
         bool packed = false;
         if (t->dtype == AI_DTYPE_F32) {
             const HeaderPack<float> hp = plan_header_pack<float>(t);
@@ -490,7 +491,7 @@ int finish_table(ai_table* t) {
             if (hp.ok) { rc = build_image<double>(t, gp, false, &image, &hp); packed = true; }
         }
         if (rc) return rc;
-        if (packed) mode = (mode == ai::kSmem) ? ai::kSmemP : ai::kSmemBankP;
+        if (packed && mode != ai::kSelect) mode = (mode == ai::kSmem) ? ai::kSmemP : ai::kSmemBankP;
     }
     t->mode = mode;
     t->copies = copies;

@@ -1,6 +1,7 @@
-// ai_inst.cuh -- explicit instantiation of eval_kernel / eval_sum_kernel for ONE (basis, dtype)
-// and every order 0..AI_MAX_ORDER, plus the order switch.  Included by the six ai_inst_*.cu
-// units so that they compile in parallel.
+// ai_inst.cuh -- explicit instantiation of eval_kernel / eval_sum_kernel / eval_multi_kernel for
+// ONE (basis, dtype) and a range of orders, plus the order switch.  Included by the twelve
+// ai_inst_*.cu units (orders 0..kSplitOrder and kSplitOrder+1..16 per basis and dtype) so that
+// they compile in parallel.
 #pragma once
 #include "ai_kernels.cuh"
 
@@ -62,7 +63,7 @@ struct Unit {
 };
 
 // compile-time unrolled switch over (order, mode)
-template <int BASIS, typename T, int ORDER = 0>
+template <int BASIS, typename T, int ORDER, int HI>
 struct Switch {
     template <typename... A> static cudaError_t eval(int order, int mode, A&&... a) {
         if (order == ORDER) {
@@ -77,7 +78,7 @@ struct Switch {
             }
             return cudaErrorInvalidValue;
         }
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::eval(order, mode, a...);
+        if constexpr (ORDER < HI) return Switch<BASIS, T, ORDER + 1, HI>::eval(order, mode, a...);
         else return cudaErrorInvalidValue;
     }
     template <typename... A> static cudaError_t sum(int order, int mode, A&&... a) {
@@ -88,7 +89,7 @@ struct Switch {
             }
             return Unit<BASIS, T, ORDER, kSmem>::sum(a...);
         }
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::sum(order, mode, a...);
+        if constexpr (ORDER < HI) return Switch<BASIS, T, ORDER + 1, HI>::sum(order, mode, a...);
         else return cudaErrorInvalidValue;
     }
     template <typename... A> static cudaError_t multi(int order, int packed, A&&... a) {
@@ -98,7 +99,7 @@ struct Switch {
             }
             return packed ? cudaErrorInvalidValue : Unit<BASIS, T, ORDER, kSmem>::multi(a...);
         }
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::multi(order, packed, a...);
+        if constexpr (ORDER < HI) return Switch<BASIS, T, ORDER + 1, HI>::multi(order, packed, a...);
         else return cudaErrorInvalidValue;
     }
     static cudaError_t prepare(int order, int mode, int smem_bytes, int* bps) {
@@ -114,7 +115,7 @@ struct Switch {
             }
             return cudaErrorInvalidValue;
         }
-        if constexpr (ORDER < kMaxOrder) return Switch<BASIS, T, ORDER + 1>::prepare(order, mode, smem_bytes, bps);
+        if constexpr (ORDER < HI) return Switch<BASIS, T, ORDER + 1, HI>::prepare(order, mode, smem_bytes, bps);
         else return cudaErrorInvalidValue;
     }
 };
@@ -122,21 +123,22 @@ struct Switch {
 }  // namespace
 }  // namespace ai
 
-#define AI_DEFINE_UNIT(NAME, BASIS, T)                                                            \
+#define AI_DEFINE_UNIT(NAME, BASIS, T, LO, HI)                                                    \
     namespace ai {                                                                                \
+    static_assert(HI <= kMaxOrder, "order range");                                                \
     cudaError_t launch_eval_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv,  \
                                    const T* x, T* y, long long n, long long head, long long nvec) { \
-        return Switch<BASIS, T>::eval(order, mode, c, tv, x, y, n, head, nvec);                   \
+        return Switch<BASIS, T, LO, HI>::eval(order, mode, c, tv, x, y, n, head, nvec);           \
     }                                                                                             \
     cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv,   \
                                   const T* x, double* r, long long n) {                           \
-        return Switch<BASIS, T>::sum(order, mode, c, tv, x, r, n);                                \
+        return Switch<BASIS, T, LO, HI>::sum(order, mode, c, tv, x, r, n);                        \
     }                                                                                             \
     cudaError_t launch_multi_##NAME(int order, int packed, const LaunchCfg& c, const MultiArgs& a, \
                                     const T* x, long long n, long long head, long long nvec) {    \
-        return Switch<BASIS, T>::multi(order, packed, c, a, x, n, head, nvec);                    \
+        return Switch<BASIS, T, LO, HI>::multi(order, packed, c, a, x, n, head, nvec);            \
     }                                                                                             \
     cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* bps) {                   \
-        return Switch<BASIS, T>::prepare(order, mode, smem_bytes, bps);                           \
+        return Switch<BASIS, T, LO, HI>::prepare(order, mode, smem_bytes, bps);                   \
     }                                                                                             \
     }

@@ -1,0 +1,3 @@
+// cheb_f64 kernels, orders 0..9 (see ai_inst.cuh)
+#include "ai_inst.cuh"
+AI_DEFINE_UNIT(cheb_f64_lo, ai::kCheb, double, 0, ai::kSplitOrder)

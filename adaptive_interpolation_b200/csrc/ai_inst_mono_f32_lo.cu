@@ -1,0 +1,3 @@
+// mono_f32 kernels, orders 0..9 (see ai_inst.cuh)
+#include "ai_inst.cuh"
+AI_DEFINE_UNIT(mono_f32_lo, ai::kMono, float, 0, ai::kSplitOrder)

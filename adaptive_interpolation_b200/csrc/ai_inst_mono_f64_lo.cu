@@ -1,0 +1,3 @@
+// mono_f64 kernels, orders 0..9 (see ai_inst.cuh)
+#include "ai_inst.cuh"
+AI_DEFINE_UNIT(mono_f64_lo, ai::kMono, double, 0, ai::kSplitOrder)

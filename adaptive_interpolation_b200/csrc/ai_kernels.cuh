@@ -886,8 +886,10 @@ struct LaunchCfg {
     const double* select;          // kSelect only: host array [mid, rec0[kMaxRecord], rec1[kMaxRecord]]
 };
 
-// One translation unit per (basis, dtype) -- see ai_inst.cuh -- each exporting:
-#define AI_DECLARE_UNIT(NAME, T)                                                                   \
+// Two translation units per (basis, dtype) -- orders 0..kSplitOrder and above, see ai_inst.cuh --
+// each exporting the four launchers below; the inline dispatchers pick the unit by order.
+constexpr int kSplitOrder = 9;
+#define AI_DECLARE_PART(NAME, T)                                                                   \
     cudaError_t launch_eval_##NAME(int order, int mode, const LaunchCfg&, const TableView&,        \
                                    const T*, T*, long long, long long, long long);                 \
     cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg&, const TableView&,         \
@@ -895,6 +897,28 @@ struct LaunchCfg {
     cudaError_t launch_multi_##NAME(int order, int packed, const LaunchCfg&, const MultiArgs&,     \
                                     const T*, long long, long long, long long);                    \
     cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* blocks_per_sm);
+#define AI_DECLARE_UNIT(NAME, T)                                                                   \
+    AI_DECLARE_PART(NAME##_lo, T)                                                                  \
+    AI_DECLARE_PART(NAME##_hi, T)                                                                  \
+    inline cudaError_t launch_eval_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv, \
+                                          const T* x, T* y, long long n, long long head, long long nvec) { \
+        return order <= kSplitOrder ? launch_eval_##NAME##_lo(order, mode, c, tv, x, y, n, head, nvec) \
+                                    : launch_eval_##NAME##_hi(order, mode, c, tv, x, y, n, head, nvec); \
+    }                                                                                              \
+    inline cudaError_t launch_sum_##NAME(int order, int mode, const LaunchCfg& c, const TableView& tv, \
+                                         const T* x, double* r, long long n) {                     \
+        return order <= kSplitOrder ? launch_sum_##NAME##_lo(order, mode, c, tv, x, r, n)          \
+                                    : launch_sum_##NAME##_hi(order, mode, c, tv, x, r, n);         \
+    }                                                                                              \
+    inline cudaError_t launch_multi_##NAME(int order, int packed, const LaunchCfg& c, const MultiArgs& a, \
+                                           const T* x, long long n, long long head, long long nvec) { \
+        return order <= kSplitOrder ? launch_multi_##NAME##_lo(order, packed, c, a, x, n, head, nvec) \
+                                    : launch_multi_##NAME##_hi(order, packed, c, a, x, n, head, nvec); \
+    }                                                                                              \
+    inline cudaError_t prepare_##NAME(int order, int mode, int smem_bytes, int* bps) {             \
+        return order <= kSplitOrder ? prepare_##NAME##_lo(order, mode, smem_bytes, bps)            \
+                                    : prepare_##NAME##_hi(order, mode, smem_bytes, bps);           \
+    }
 AI_DECLARE_UNIT(cheb_f32, float)
 AI_DECLARE_UNIT(cheb_f64, double)
 AI_DECLARE_UNIT(leg_f32, float)
@@ -902,5 +926,6 @@ AI_DECLARE_UNIT(leg_f64, double)
 AI_DECLARE_UNIT(mono_f32, float)
 AI_DECLARE_UNIT(mono_f64, double)
 #undef AI_DECLARE_UNIT
+#undef AI_DECLARE_PART
 
 }  // namespace ai
