@@ -422,14 +422,24 @@ int finish_table(ai_table* t) {
         return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
                     t->device, prop.major, prop.minor);
     t->sm_count = prop.sm_count;
-    const size_t smem_cap = prop.smem_optin;
+    size_t smem_cap = prop.smem_optin;
+    if (const char* e = std::getenv("AI_B200_SMEM_CAP_KB")) {            // test / tuning hook
+        const long kb = std::atol(e);
+        if (kb >= 16 && (size_t)kb * 1024 < smem_cap) smem_cap = (size_t)kb * 1024;
+    }
 
-    // build the packed (shared-memory) image first; if it cannot be staged, rebuild it in the
-    // global layout (16-byte padded records)
+    // Build the shared-memory image first -- with the one-word record header when every leaf
+    // qualifies (bit-identical values, one shared-memory wavefront less per 32 points, two in
+    // fp64, and a shorter record) -- and if it cannot be staged rebuild it in the global layout
+    // (16-byte padded records, two-element header).
     const char* force = std::getenv("AI_B200_FORCE_MODE");                // test hook
     const int forced = force ? std::atoi(force) : -1;
     std::vector<unsigned char> image;
-    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image) : build_image<double>(t, gp, false, &image);
+    HeaderPack<float> hp32;
+    HeaderPack<double> hp64;
+    if (t->dtype == AI_DTYPE_F32) hp32 = plan_header_pack<float>(t); else hp64 = plan_header_pack<double>(t);
+    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32)
+                                    : build_image<double>(t, gp, false, &image, &hp64);
     if (rc) return rc;
     const bool go_global = (forced == ai::kGlobal) || ((size_t)t->view.image_bytes > smem_cap);
     if (go_global) {
@@ -465,34 +475,29 @@ int finish_table(ai_table* t) {
     }
     if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
     // two leaves: both records ride in the kernel parameters, element-wise select instead of a gather
+    // (the image stays: the reduction and multi-table kernels read it)
     if (!go_global && ((L == 2 && forced < 0) || (L <= 2 && forced == ai::kSelect))) {
         mode = ai::kSelect; copies = 1;
-        const int nrec = t->order + 1 + ((t->basis == ai::kMono) ? 0 : 2);
+        const int hdr = (t->basis == ai::kMono) ? 0 : 2;
         t->select.assign(1 + 2 * ai::kMaxRecord, 0.0);
         t->select[0] = (L == 2) ? t->breaks[1] : std::numeric_limits<double>::infinity();
         for (int i = 0; i < 2; ++i) {
             const int64_t leaf = std::min<int64_t>(i, L - 1);
-            const unsigned char* rec = image.data() + t->view.off_records + (size_t)leaf * t->rstride * esz;
-            for (int k = 0; k < nrec; ++k)
-                t->select[1 + i * ai::kMaxRecord + k] = (t->dtype == AI_DTYPE_F32)
-                    ? (double)reinterpret_cast<const float*>(rec)[k] : reinterpret_cast<const double*>(rec)[k];
+            double* rec = &t->select[1 + i * ai::kMaxRecord];
+            if (hdr) {           // the values build_image stores: a and 2/(b-a) in table-dtype arithmetic
+                if (t->dtype == AI_DTYPE_F32) {
+                    const float a = (float)t->breaks[leaf], b = (float)t->breaks[leaf + 1];
+                    rec[0] = a; rec[1] = 2.0f / (b - a);
+                } else {
+                    const double a = t->breaks[leaf], b = t->breaks[leaf + 1];
+                    rec[0] = a; rec[1] = 2.0 / (b - a);
+                }
+            }
+            for (int k = 0; k <= t->order; ++k) rec[hdr + k] = t->coef[(size_t)leaf * (t->order + 1) + k];
         }
     }
-    // one-element record header where the table allows it (bit-identical values, one shared-memory
-    // wavefront less per 32 points; two less in fp64)
-    // (a kSelect table keeps a packed image too: the reduction and multi-table kernels read it)
-    if (mode == ai::kSmem || mode == ai::kSmemBank || mode == ai::kSelect) {
-        bool packed = false;
-        if (t->dtype == AI_DTYPE_F32) {
-            const HeaderPack<float> hp = plan_header_pack<float>(t);
-            if (hp.ok) { rc = build_image<float>(t, gp, false, &image, &hp); packed = true; }
-        } else {
-            const HeaderPack<double> hp = plan_header_pack<double>(t);
-            if (hp.ok) { rc = build_image<double>(t, gp, false, &image, &hp); packed = true; }
-        }
-        if (rc) return rc;
-        if (packed && mode != ai::kSelect) mode = (mode == ai::kSmem) ? ai::kSmemP : ai::kSmemBankP;
-    }
+    if (t->packed && mode == ai::kSmem) mode = ai::kSmemP;
+    if (t->packed && mode == ai::kSmemBank) mode = ai::kSmemBankP;
     t->mode = mode;
     t->copies = copies;
     t->view.copies = copies;
@@ -688,8 +693,12 @@ int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* st
     if (t->mode == ai::kGlobal) {
         ai::index_kernel<T, ai::kGlobal><<<grid, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
     } else {
-        if (t->aux_smem > 48 * 1024)
-            AI_CUDA(cudaFuncSetAttribute(ai::index_kernel<T, ai::kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->aux_smem));
+        if (t->aux_smem > 48 * 1024) {
+            cudaFuncAttributes fa;
+            AI_CUDA(cudaFuncGetAttributes(&fa, ai::index_kernel<T, ai::kSmem>));
+            if (fa.maxDynamicSharedSizeBytes < t->aux_smem)
+                AI_CUDA(cudaFuncSetAttribute(ai::index_kernel<T, ai::kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->aux_smem));
+        }
         ai::index_kernel<T, ai::kSmem><<<grid, ai::kBlock, t->aux_smem, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
     }
     AI_CUDA(cudaGetLastError());

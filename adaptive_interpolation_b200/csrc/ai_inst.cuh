@@ -10,6 +10,19 @@ namespace {
 
 constexpr int kMaxOrder = 16;
 
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The limit is per kernel FUNCTION, not
+// per table: only ever raise it, so a later, smaller table of the same (basis, order, dtype, mode)
+// cannot take the room of an earlier, larger one away.
+template <typename K>
+cudaError_t raise_smem_limit(K kernel, int smem_bytes) {
+    if (smem_bytes <= 48 * 1024) return cudaSuccess;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    if (fa.maxDynamicSharedSizeBytes >= smem_bytes) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+
 template <int BASIS, typename T, int ORDER, int MODE>
 struct Unit {
     static cudaError_t eval(const LaunchCfg& c, const TableView& tv, const T* x, T* y,
@@ -37,25 +50,17 @@ struct Unit {
     static cudaError_t multi(const LaunchCfg& c, const MultiArgs& a, const T* x, long long n, long long head,
                              long long nvec) {
         constexpr bool PK = mode_packed_hdr(MODE);
-        if (c.smem_bytes > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(eval_multi_kernel<BASIS, ORDER, T, PK>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = raise_smem_limit(eval_multi_kernel<BASIS, ORDER, T, PK>, c.smem_bytes);
+        if (e != cudaSuccess) return e;
         eval_multi_kernel<BASIS, ORDER, T, PK><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(a, x, n, head, nvec);
         return cudaGetLastError();
     }
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
-        cudaError_t e;
-        if (smem_bytes > 48 * 1024) {
-            e = cudaFuncSetAttribute(eval_kernel<BASIS, ORDER, T, MODE>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = raise_smem_limit(eval_kernel<BASIS, ORDER, T, MODE>, smem_bytes);
+        if (e != cudaSuccess) return e;
+        if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kGlobal) {
+            e = raise_smem_limit(eval_sum_kernel<BASIS, ORDER, T, MODE>, smem_bytes);
             if (e != cudaSuccess) return e;
-            if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kGlobal) {
-                e = cudaFuncSetAttribute(eval_sum_kernel<BASIS, ORDER, T, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-                if (e != cudaSuccess) return e;
-            }
         }
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<BASIS, ORDER, T, MODE>,
                                                              kBlock, smem_bytes);

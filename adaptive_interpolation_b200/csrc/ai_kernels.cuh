@@ -297,6 +297,17 @@ template <int BASIS, int ORDER, typename T> struct Record {
         const T w = rec[0];
 #pragma unroll
         for (int k = 0; k <= ORDER; ++k) v[2 + k] = rec[(1 + k) * STRIDE];
+        unpack_header(w, s0_hi, s0_lo);
+    }
+    // run-time element stride (kSmemBankN)
+    __device__ __forceinline__ void load_packed_strided(const T* __restrict__ rec, int stride, unsigned s0_hi,
+                                                        unsigned s0_lo) {
+        const T w = rec[0];
+#pragma unroll
+        for (int k = 0; k <= ORDER; ++k) v[2 + k] = rec[(1 + k) * stride];
+        unpack_header(w, s0_hi, s0_lo);
+    }
+    __device__ __forceinline__ void unpack_header(T w, unsigned s0_hi, unsigned s0_lo) {
         if constexpr (sizeof(T) == 4) {
             const unsigned u = __float_as_uint(w);
             v[0] = __uint_as_float(u & 0xFFFFFE00u);
@@ -449,7 +460,31 @@ __device__ __forceinline__ T eval_leaf(const T* __restrict__ rec, T x, T inv_ord
 }
 
 // ------------------------------------------------------------------------- streaming access
+#ifndef AI_LD_MODE
+#define AI_LD_MODE 1               // 0: ld.global.cs, 1: ld.global.L1::no_allocate (LDG.E.NA: measured equal or better everywhere, +5 points on sorted input when the table leaves < 32 KB of L1), 2: ld.global.nc.L1::no_allocate
+#endif
+#if AI_LD_MODE == 0
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+#else
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 v;
+#if AI_LD_MODE == 1
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#endif
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 v;
+#if AI_LD_MODE == 1
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#endif
+    return v;
+}
+#endif
 template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
 
 // Make the table addressable for this CTA and return its base.  kSmem: copy the packed image
@@ -501,7 +536,9 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     constexpr bool PK = mode_packed_hdr(MODE);                     // one-element record header
     // copies per record element: compile-time except in kSmemBankN
     const int cp = (MODE == kSmemBankN) ? tv.copies : Copies<T, MODE>::value;
-    const int R = rec_stride_for<BASIS, ORDER, T, MODE>() * cp;    // record stride in elements
+    // record stride in elements (kSmemBankN: packed or unpacked header, decided per table)
+    const int R = ((MODE == kSmemBankN && Record<BASIS, ORDER, T>::HDR == 2 && tv.s0_hi)
+                       ? rec_stride_packed(ORDER) : rec_stride_for<BASIS, ORDER, T, MODE>()) * cp;
     // bank-private layout: lane l reads copy l mod cp of every element
     const T* records = reinterpret_cast<const T*>(base + (kBank ? tv.soff_records : tv.off_records))
                        + (threadIdx.x & (cp - 1));
@@ -518,7 +555,16 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
             if constexpr (VEC) r.load_vec(p);
             else if constexpr (PK) r.template load_packed<Copies<T, MODE>::value>(p, tv.s0_hi, tv.s0_lo);
             else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);
-            else if constexpr (MODE == kSmemBankN) r.load_strided(p, cp);
+            else if constexpr (MODE == kSmemBankN) {
+                // partial replication serves packed and unpacked headers (warp-uniform branch);
+                // s0_hi is S0's high word, never 0 for a packed table
+                if constexpr (Record<BASIS, ORDER, T>::HDR == 2) {
+                    if (tv.s0_hi) r.load_packed_strided(p, cp, tv.s0_hi, tv.s0_lo);
+                    else r.load_strided(p, cp);
+                } else {
+                    r.load_strided(p, cp);
+                }
+            }
             else r.template load<1>(p);
         }
     };

@@ -185,7 +185,7 @@ def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
     """Dyadic tables carry [a, 2/(b-a)] as one word (a's bits | exponent offset); the two integer
     instructions that unpack it must reproduce the stored header exactly, so values are the same
@@ -197,11 +197,12 @@ def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
     info_p = tab_p.info()
     if not info_p["header_packed"]:
         pytest.skip("table does not qualify for the packed header")
-    assert info_p["residency"] in (0, 1, 4)
+    assert info_p["residency"] in (0, 1, 3, 4)
     monkeypatch.setenv("AI_B200_NO_PACKED_HDR", "1")
     tab_u = dev_table(name)
     info_u = tab_u.info()
-    assert not info_u["header_packed"] and info_u["residency"] == info_p["residency"]
+    assert not info_u["header_packed"]
+    assert info_u["residency"] == info_p["residency"] or mode == 1      # 32 (16) unpacked copies may not fit
     assert info_p["record_stride"] <= info_u["record_stride"]
     lo, hi = float(g.lower_bound), float(g.upper_bound)
     x = np.concatenate([g.x, np.random.default_rng(9).uniform(lo, hi, 1 << 18).astype(g.dtype)])
@@ -225,7 +226,7 @@ def test_saved_tables_take_the_packed_header():
     qualifies; the deep config-4 trees (breakpoints with > 15 significant bits) do not."""
     for name in SAVED:
         info = dev_table(name).info()
-        assert info["header_packed"] == (1 if info["residency"] in (0, 1, 4) else 0), (name, info)
+        assert info["header_packed"] == 1, (name, info)
     assert dev_table("gen__cfg3_j0_cheb_o13_f64").info()["header_packed"] == 1
     assert dev_table("gen__cfg4_f1_leg_o7_f32").info()["header_packed"] == 0
 
