@@ -22,7 +22,7 @@ MAX_MULTI = 4
 # every symbol include/ai_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "ai_last_error", "ai_version", "ai_device_count", "ai_device_sm_arch",
-    "ai_table_create", "ai_table_create_from_tree", "ai_table_destroy", "ai_table_get_info",
+    "ai_table_create", "ai_table_create_from_tree", "ai_table_plan", "ai_table_destroy", "ai_table_get_info",
     "ai_table_get_flat",
     "ai_eval_f32", "ai_eval_f64", "ai_eval_index_f32", "ai_eval_index_f64",
     "ai_eval_sum_f32", "ai_eval_sum_f64", "ai_eval_multi_f32", "ai_eval_multi_f64",
@@ -76,6 +76,7 @@ def lib():
     L.ai_device_sm_arch.argtypes = [i32] + [ctypes.POINTER(ctypes.c_int)] * 3
     L.ai_table_create.argtypes = [i32, i32, i32, i64, vp, vp, i32, ctypes.POINTER(vp)]
     L.ai_table_create_from_tree.argtypes = [i32, i32, i32, i32, i32, vp, i64, i32, ctypes.POINTER(vp)]
+    L.ai_table_plan.argtypes = [i32, i32, i32, i64, vp, vp, i64, ctypes.POINTER(TableInfo)]
     L.ai_table_destroy.argtypes = [vp]
     L.ai_table_get_info.argtypes = [vp, ctypes.POINTER(TableInfo)]
     L.ai_table_get_flat.argtypes = [vp, vp, vp]

@@ -395,7 +395,11 @@ int prepare_dispatch(int basis, int dtype, int order, int mode, int smem, int* b
     return AI_OK;
 }
 
-int finish_table(ai_table* t) {
+// Everything about a table that is decided on the HOST, without touching CUDA: validation, the
+// lookup grid, the record layout and the residency mode for a device with `smem_cap` bytes of
+// opt-in shared memory per CTA.  Fills `t` and the packed image.  (Exposed as ai_table_plan so
+// that the CPU-only test tier covers this logic.)
+int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_out) {
     // validate the flattened table
     const int64_t L = t->L;
     for (int64_t k = 0; k <= L; ++k)
@@ -413,16 +417,6 @@ int finish_table(ai_table* t) {
     if (rc) return rc;
     t->G = gp.G; t->p = gp.p; t->K = gp.K; t->g0 = gp.g0;
 
-    DeviceGuard guard(t->device);
-    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
-    DeviceInfo prop;
-    rc = device_info(t->device, &prop);
-    if (rc) return rc;
-    if (prop.major < 10)
-        return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
-                    t->device, prop.major, prop.minor);
-    t->sm_count = prop.sm_count;
-    size_t smem_cap = prop.smem_optin;
     if (const char* e = std::getenv("AI_B200_SMEM_CAP_KB")) {            // test / tuning hook
         const long kb = std::atol(e);
         if (kb >= 16 && (size_t)kb * 1024 < smem_cap) smem_cap = (size_t)kb * 1024;
@@ -434,7 +428,7 @@ int finish_table(ai_table* t) {
     // (16-byte padded records, two-element header).
     const char* force = std::getenv("AI_B200_FORCE_MODE");                // test hook
     const int forced = force ? std::atoi(force) : -1;
-    std::vector<unsigned char> image;
+    std::vector<unsigned char>& image = *image_out;
     HeaderPack<float> hp32;
     HeaderPack<double> hp64;
     if (t->dtype == AI_DTYPE_F32) hp32 = plan_header_pack<float>(t); else hp64 = plan_header_pack<double>(t);
@@ -507,10 +501,7 @@ int finish_table(ai_table* t) {
     if (ai::mode_bank(mode))
         t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
     t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
-    AI_CUDA(cudaMalloc(&t->d_image, image.size()));
-    AI_CUDA(cudaMemcpy(t->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
-
-    t->view.image = static_cast<const unsigned char*>(t->d_image);
+    t->view.image = nullptr;
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
@@ -526,6 +517,26 @@ int finish_table(ai_table* t) {
     // adapt.py:107 `*(1./n)`: 1./n in double, then rounded to the table dtype by the multiply
     const double inv = t->order > 0 ? 1.0 / (double)t->order : 0.0;
     t->view.inv_order = (t->dtype == AI_DTYPE_F32) ? (double)(float)inv : inv;
+    return AI_OK;
+}
+
+// plan on the host, then stage the image on the table's device and prepare its kernels
+int finish_table(ai_table* t) {
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
+    DeviceInfo prop;
+    int rc = device_info(t->device, &prop);
+    if (rc) return rc;
+    if (prop.major < 10)
+        return fail(AI_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    t->device, prop.major, prop.minor);
+    t->sm_count = prop.sm_count;
+    std::vector<unsigned char> image;
+    rc = plan_table(t, prop.smem_optin, &image);
+    if (rc) return rc;
+    AI_CUDA(cudaMalloc(&t->d_image, image.size()));
+    AI_CUDA(cudaMemcpy(t->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
+    t->view.image = static_cast<const unsigned char*>(t->d_image);
 
     int bps = 0;
     rc = prepare_dispatch(t->basis, t->dtype, t->order, t->mode, t->eval_smem, &bps);
@@ -540,10 +551,16 @@ int finish_table(ai_table* t) {
     return AI_OK;
 }
 
-int check_common(int basis, int order, int dtype, int device) {
+int check_shape(int basis, int order, int dtype) {
     if (basis < 0 || basis > 2) return fail(AI_ERR_INVALID, "basis %d not in {0 chebyshev, 1 legendre, 2 monomial}", basis);
     if (order < 0 || order > AI_MAX_ORDER) return fail(AI_ERR_INVALID, "order %d not in [0, %d]", order, AI_MAX_ORDER);
     if (dtype != AI_DTYPE_F32 && dtype != AI_DTYPE_F64) return fail(AI_ERR_INVALID, "dtype %d not in {0 f32, 1 f64}", dtype);
+    return AI_OK;
+}
+
+int check_common(int basis, int order, int dtype, int device) {
+    int rc = check_shape(basis, order, dtype);
+    if (rc) return rc;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
@@ -878,14 +895,8 @@ int ai_device_sm_arch(int device, int* major, int* minor, int* sm_count) {
     return AI_OK;
 }
 
-int ai_table_create(int basis, int order, int dtype, int64_t n_leaves, const void* breaks,
-                    const void* coef, int device, ai_table_t** out) {
-    if (!out) return fail(AI_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    int rc = check_common(basis, order, dtype, device);
-    if (rc) return rc;
-    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
-    if (!breaks || !coef) return fail(AI_ERR_INVALID, "breaks or coef is NULL");
+static ai_table* table_from_flat(int basis, int order, int dtype, int64_t n_leaves, const void* breaks,
+                                 const void* coef, int device) {
     ai_table* t = new ai_table;
     t->basis = basis; t->order = order; t->dtype = dtype; t->device = device; t->L = n_leaves;
     t->breaks.resize(n_leaves + 1);
@@ -901,10 +912,41 @@ int ai_table_create(int basis, int order, int dtype, int64_t n_leaves, const voi
         for (int64_t k = 0; k <= n_leaves; ++k) t->breaks[k] = b[k];
         for (size_t k = 0; k < t->coef.size(); ++k) t->coef[k] = c[k];
     }
+    return t;
+}
+
+int ai_table_create(int basis, int order, int dtype, int64_t n_leaves, const void* breaks,
+                    const void* coef, int device, ai_table_t** out) {
+    if (!out) return fail(AI_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_common(basis, order, dtype, device);
+    if (rc) return rc;
+    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
+    if (!breaks || !coef) return fail(AI_ERR_INVALID, "breaks or coef is NULL");
+    ai_table* t = table_from_flat(basis, order, dtype, n_leaves, breaks, coef, device);
     rc = finish_table(t);
     if (rc) { ai_table_destroy(t); return rc; }
     *out = t;
     return AI_OK;
+}
+
+int ai_table_plan(int basis, int order, int dtype, int64_t n_leaves, const void* breaks, const void* coef,
+                  int64_t smem_cap_bytes, ai_table_info_t* info) {
+    if (!info) return fail(AI_ERR_INVALID, "info is NULL");
+    int rc = check_shape(basis, order, dtype);
+    if (rc) return rc;
+    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
+    if (!breaks || !coef) return fail(AI_ERR_INVALID, "breaks or coef is NULL");
+    if (smem_cap_bytes <= 0) smem_cap_bytes = 227 * 1024;        // sm_100: opt-in shared memory per CTA
+    ai_table* t = table_from_flat(basis, order, dtype, n_leaves, breaks, coef, -1);
+    std::vector<unsigned char> image;
+    rc = plan_table(t, (size_t)smem_cap_bytes, &image);
+    if (rc == AI_OK) {
+        t->blocks_per_sm = 0; t->sm_count = 0;
+        rc = ai_table_get_info(t, info);
+    }
+    delete t;
+    return rc;
 }
 
 int ai_table_create_from_tree(int basis, int order, int dtype, int num_levels, int layout,

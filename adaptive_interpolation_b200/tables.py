@@ -216,6 +216,17 @@ def load_golden(name):
     return GoldenRecord(os.path.join(_GOLDEN_DIR, name + ".npz"))
 
 
+def plan(flat, smem_cap_bytes=0):
+    """Host-only dry run of the table construction (ai_table_plan): lookup grid, record layout and
+    residency mode the library would choose, as a dict.  Needs no GPU."""
+    info = _cabi.TableInfo()
+    _cabi.check(_cabi.lib().ai_table_plan(
+        _cabi.BASIS_IDS[flat.basis], flat.order,
+        _cabi.DTYPE_F32 if flat.dtype == np.float32 else _cabi.DTYPE_F64,
+        flat.n_leaves, flat.breaks.ctypes.data, flat.coef.ctypes.data, int(smem_cap_bytes), ctypes.byref(info)))
+    return info.as_dict()
+
+
 # ------------------------------------------------------------------------- device tables
 class DeviceTable(object):
     """Owns one ai_table_t handle (a table resident on one GPU)."""

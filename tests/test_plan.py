@@ -1,0 +1,113 @@
+"""The table planner (host side of ai_table_create) through ai_table_plan: lookup grid, record
+layout and residency mode for every golden table, without a GPU.  What the plan promises is
+checked on the device by tests/test_gpu_parity.py; here the decisions themselves are pinned."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from adaptive_interpolation_b200 import _cabi, build, tables
+from conftest import all_golden_names, golden
+
+NAMES = all_golden_names()
+SAVED = [n for n in NAMES if n.startswith("approx")]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def lib():
+    build.build()
+    return _cabi.lib()
+
+
+def plan(name, **kw):
+    return tables.plan(tables.flatten(golden(name)), **kw)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_plan_is_consistent(name):
+    f = tables.flatten(golden(name))
+    info = tables.plan(f)
+    assert info["n_leaves"] == f.n_leaves and info["order"] == f.order and info["device"] == -1
+    assert info["lower_bound"] == float(f.breaks[0]) and info["upper_bound"] == float(f.breaks[-1])
+    assert 1 <= info["grid_cells"] <= (1 << 20)
+    assert info["smem_bytes"] <= 227 * 1024
+    assert info["residency"] in (0, 1, 2, 3, 4)
+    if info["residency"] == 4:
+        assert f.n_leaves == 2 and info["smem_bytes"] == 0
+    if info["residency"] in (1, 3):
+        assert info["bank_copies"] >= 2 and f.n_leaves > (32 if f.dtype == np.float32 else 16)
+    if info["lookup_mode"] == 2:                       # in-register bitmap rank
+        assert info["search_steps"] == 0
+    hdr = 0 if f.basis == "monomial" else (1 if info["header_packed"] else 2)
+    assert info["record_stride"] >= f.order + 1 + hdr
+
+
+def test_saved_tables_plan():
+    """All 27 saved approximations: exact grid (no search), staged in shared memory, one-word header."""
+    for name in SAVED:
+        info = plan(name)
+        assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
+        assert info["header_packed"] == 1 and info["image_bytes"] <= 48 * 1024, (name, info)
+    assert plan("approx__32o6-p1.19209289551e-06")["lookup_mode"] == 2          # BASELINE configs[1]
+    assert plan("approx__32o6-p1.19209289551e-06")["residency"] == 0
+    assert plan("approx__32o3-p1.19209289551e-06")["residency"] == 1            # 62 leaves > 32 banks
+    assert plan("approx__64o13-p1.19209289551e-06")["residency"] == 4           # two leaves: select
+    big = plan("approximations__64o5-p2.22044604925e-14")                       # 429 leaves
+    assert big["residency"] == 3 and big["bank_copies"] == 8
+
+
+def test_config_tables_plan():
+    cfg3 = plan("gen__cfg3_j0_cheb_o13_f64")
+    assert cfg3["lookup_mode"] == 2 and cfg3["header_packed"] == 1 and cfg3["residency"] == 0
+    for name, k in (("gen__cfg4_f1_leg_o7_f32", 4), ("gen__cfg4_f1_leg_o7_f64", 6)):
+        info = plan(name)                               # deep skewed trees: grid + bounded search
+        assert info["search_steps"] == k and info["lookup_mode"] == 1 and info["header_packed"] == 0
+
+
+def test_smaller_shared_memory_changes_the_residency():
+    name = "approximations__64o5-p2.22044604925e-14"
+    assert plan(name, smem_cap_bytes=160 * 1024)["bank_copies"] == 4
+    assert plan(name, smem_cap_bytes=20 * 1024)["residency"] == 2               # does not fit: L2-resident
+    assert plan(name, smem_cap_bytes=20 * 1024)["header_packed"] == 0           # global layout keeps [a, s]
+
+
+def test_hooks(monkeypatch):
+    name = "approx__32o6-p1.19209289551e-06"
+    monkeypatch.setenv("AI_B200_NO_PACKED_HDR", "1")
+    assert plan(name)["header_packed"] == 0
+    monkeypatch.delenv("AI_B200_NO_PACKED_HDR")
+    monkeypatch.setenv("AI_B200_NO_RANK", "1")
+    assert plan(name)["lookup_mode"] == 0
+    monkeypatch.delenv("AI_B200_NO_RANK")
+    monkeypatch.setenv("AI_B200_MAX_CELLS", "8")                                 # grid too coarse: search follows
+    info = plan(name)
+    assert info["grid_cells"] <= 8 and info["search_steps"] >= 1 and info["lookup_mode"] == 1
+    monkeypatch.delenv("AI_B200_MAX_CELLS")
+    for mode in (0, 1, 2):
+        monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
+        assert plan(name)["residency"] == mode
+
+
+def test_large_tables_plan():
+    """Beyond 65536 leaves the grid grows with the table (one L2 access instead of a long search)."""
+    for n_leaves, k0 in ((131072, True), (100000, False)):
+        br = np.linspace(0.0, 16.0, n_leaves + 1)
+        f = tables.FlatTable("chebyshev", 3, np.float64, br, np.zeros((n_leaves, 4)))
+        info = tables.plan(f)
+        assert info["residency"] == 2 and info["smem_resident"] == 0
+        assert (info["search_steps"] == 0) == k0 and info["search_steps"] <= 2
+        assert info["grid_cells"] >= n_leaves
+
+
+def test_rejects_malformed_tables(lib):
+    info = _cabi.TableInfo()
+    br = np.array([0.0, 2.0, 1.0, 3.0])
+    co = np.zeros(3 * 4)
+    assert lib.ai_table_plan(0, 3, 1, 3, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(info)) == 2     # AI_ERR_TABLE
+    assert b"strictly increasing" in lib.ai_last_error()
+    br = np.array([0.0, np.inf])
+    assert lib.ai_table_plan(0, 3, 1, 1, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(info)) == 2
+    assert lib.ai_table_plan(0, 3, 1, 0, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(info)) == 2
+    assert lib.ai_table_plan(0, 3, 1, 1, None, None, 0, ctypes.byref(info)) == 1                         # AI_ERR_INVALID
+    assert lib.ai_table_plan(0, 3, 1, 1, br.ctypes.data, co.ctypes.data, 0, None) == 1
+    assert lib.ai_table_plan(9, 3, 1, 1, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(info)) == 1
