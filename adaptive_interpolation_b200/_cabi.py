@@ -41,7 +41,7 @@ class TableInfo(ctypes.Structure):
         ("smem_resident", ctypes.c_int32), ("lookup_mode", ctypes.c_int32), ("block_threads", ctypes.c_int32),
         ("blocks_per_sm", ctypes.c_int32), ("sm_count", ctypes.c_int32),
         ("lower_bound", ctypes.c_double), ("upper_bound", ctypes.c_double),
-        ("header_packed", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("header_packed", ctypes.c_int32), ("cell_records", ctypes.c_int32),
     ]
 
     def as_dict(self):

@@ -120,6 +120,7 @@ struct ai_table {
     int mode = ai::kSmem;              // table residency: kSmem / kSmemBank / kGlobal / kSmemBankN
     int copies = 1;                    // bank modes: copies per element
     int packed = 0;                    // 1: records carry the one-element header (modes kSmemP / kSmemBankP)
+    int cell_records = 0;              // 1: one record per coarse cell (view.rank_mode 2)
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
@@ -139,6 +140,7 @@ struct GridPlan {
     int rank_mode = 0;
     unsigned div_mul = 0, div_shift = 0, div_add = 0;
     unsigned cont = 0;
+    std::vector<uint32_t> coarse_leaf;   // rank mode: leaf of every coarse cell
 };
 
 long long gcd_ll(long long a, long long b) {
@@ -183,6 +185,8 @@ void plan_rank(const std::vector<double>& b, GridPlan* gp) {
         if (leaf != (int)gp->first[g]) return;
     }
     gp->rank_mode = 1; gp->div_mul = mul; gp->div_shift = sh; gp->div_add = add; gp->cont = cont;
+    gp->coarse_leaf.resize((size_t)Gc);
+    for (long long c = 0; c < Gc; ++c) gp->coarse_leaf[(size_t)c] = gp->first[(size_t)(c * q)];
 }
 
 bool cells_for(const std::vector<double>& b, int p, long long* g0, long long* glast) {
@@ -333,6 +337,13 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     const int n = t->order;
     const int64_t L = t->L;
     const bool packed = pack && pack->ok && !global_layout;
+    // Records once per COARSE CELL instead of once per leaf (rank_mode 2): the cell index the
+    // lookup computes anyway addresses the record and the rank is never formed.  Only while the
+    // cells, like the leaves, fit one per bank (32 / 16), so that gathers stay conflict-free.
+    const int64_t Gc = (int64_t)gp.coarse_leaf.size();
+    const bool cell_records = gp.rank_mode && Gc >= L && Gc <= (sizeof(T) == 4 ? 32 : 16)
+                              && !std::getenv("AI_B200_NO_CELL_RECORDS");
+    const int64_t NR = cell_records ? Gc : L;            // records stored
     const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T))
                                 : (packed ? ai::rec_stride_packed(n) : ai::rec_stride(t->basis, n));
     const int hdr = (t->basis == ai::kMono) ? 0 : (packed ? 1 : 2);
@@ -341,7 +352,7 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     const int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
     const int off_breaks = round_up16((size_t)gp.G * (size_t)(4 >> fshift));
     const int off_records = off_breaks + round_up16((size_t)(L + 1 + pad) * sizeof(T));
-    const size_t total = (size_t)off_records + (size_t)round_up16((size_t)L * R * sizeof(T));
+    const size_t total = (size_t)off_records + (size_t)round_up16((size_t)NR * R * sizeof(T));
     image->assign(total, 0);
     if (fshift == 2) {
         for (int g = 0; g < gp.G; ++g) (*image)[off_first + g] = (unsigned char)gp.first[g];
@@ -356,8 +367,9 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     for (int64_t k = 0; k <= L; ++k) br[k] = (T)t->breaks[k];
     for (int k = 0; k < pad; ++k) br[L + 1 + k] = std::numeric_limits<T>::infinity();
     T* rec = reinterpret_cast<T*>(image->data() + off_records);
-    for (int64_t i = 0; i < L; ++i) {
-        T* r = rec + i * R;
+    for (int64_t ri = 0; ri < NR; ++ri) {
+        const int64_t i = cell_records ? (int64_t)gp.coarse_leaf[(size_t)ri] : ri;      // the leaf stored here
+        T* r = rec + ri * R;
         if (hdr == 2) {
             const T a = (T)t->breaks[i], b = (T)t->breaks[i + 1];
             r[0] = a;
@@ -372,7 +384,9 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     t->view.s0_hi = packed ? pack->s0_hi : 0;
     t->view.s0_lo = packed ? pack->s0_lo : 0;
     t->view.image_bytes = (int)total;
-    t->view.n_records_elems = (int)(L * R);
+    t->view.n_records_elems = (int)(NR * R);
+    t->view.n_records = (int)NR;
+    t->cell_records = cell_records ? 1 : 0;
     t->view.n_breaks_elems = (int)(L + 1 + pad);
     t->view.off_first = off_first;
     t->view.off_breaks = off_breaks;
@@ -505,7 +519,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
-    t->view.rank_mode = gp.rank_mode;
+    t->view.rank_mode = gp.rank_mode ? (t->cell_records ? 2 : 1) : 0;
     t->view.div_mul = gp.div_mul;
     t->view.div_shift = gp.div_shift;
     t->view.div_add = gp.div_add;
@@ -1041,6 +1055,7 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->smem_bytes = t->eval_smem;
     info->residency = (t->mode == ai::kSmemP) ? ai::kSmem : (t->mode == ai::kSmemBankP ? ai::kSmemBank : t->mode);
     info->header_packed = t->packed;
+    info->cell_records = t->cell_records;
     info->bank_copies = t->copies;
     info->smem_resident = t->smem_resident;
     info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : 0);

@@ -110,7 +110,9 @@ struct TableView {
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
     int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit, 0 -> 32-bit
-    int rank_mode;                 // 1: leaf = rank in cont_mask of the coarse cell (no table read)
+    int rank_mode;                 // 1: leaf = rank in cont_mask of the coarse cell (no table read);
+                                   // 2: as 1, and rec[] holds one record per COARSE CELL (n_records of them)
+    int n_records;                 // records in rec[]: L, or the coarse cell count in rank_mode 2
     unsigned div_mul, div_shift;   // coarse cell = (fine cell * div_mul) >> div_shift  (exact / q)
     unsigned div_add;              // -g0 * div_mul (mod 2^32): folds the "- g0" into the multiply
     unsigned cont_mask;            // bit c set: coarse cell c continues the leaf of cell c-1 (<= 32 cells)
@@ -213,18 +215,30 @@ template <typename T> struct Lookup {
     // dyadic tables with <= 32 coarse cells: no memory access at all.  The coarse cell is the
     // fine cell divided by the odd factor q of the leaf width (exact multiply-shift, verified on
     // the host for every fine cell); the leaf is the number of leaf starts at or before it.
-    __device__ __forceinline__ int rank_guess(T x) const {
+    __device__ __forceinline__ unsigned coarse_cell(T x) const {
         const unsigned c = (cell_abs(x) * div_mul + div_add) >> div_shift;
         AI_CHECK(c < 32u);
+        return c;
+    }
+    __device__ __forceinline__ int rank_guess(T x) const {
+        const unsigned c = coarse_cell(x);
         const unsigned above = 0xfffffffeu << c;                 // bits strictly above c
         const int i = (int)c - __popc(cont & ~above);
         AI_CHECK(i >= 0 && i <= lmax);
         return i;
     }
-    // leaf ordinals of N points held in registers.  Mode branches are warp-uniform and sit
-    // OUTSIDE the per-point loops, so the N dependent chains interleave (ILP).
+    // RECORD index of N points held in registers: the leaf ordinal, except for tables whose
+    // records are stored once per coarse cell (rank_mode 2: at most 32 / 16 cells), where the
+    // coarse cell itself addresses the record and the rank (shift, mask, popc, subtract) is not
+    // computed at all.  Mode branches are warp-uniform and sit OUTSIDE the per-point loops, so the
+    // N dependent chains interleave (ILP).
     template <int N>
     __device__ __forceinline__ void leaves(const T (&x)[N], int (&i)[N]) const {
+        if (rank_mode == 2) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) i[e] = (int)coarse_cell(x[e]);
+            return;
+        }
         if (rank_mode) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = rank_guess(x[e]);
@@ -269,7 +283,7 @@ template <typename T> struct Lookup {
     // as leaf(), but also reproduces the reference for NaN: every `mid > x` test is false, the
     // walk always goes right and ends on the last leaf (approximator.py:287-290).
     __device__ __forceinline__ int leaf_nan_exact(T x) const {
-        int i = leaf(x);
+        const int i = rank_mode ? rank_guess(x) : leaf(x);      // the LEAF, also when records are per cell
         return (x != x) ? lmax : i;
     }
 };
@@ -546,7 +560,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     const T inv_order = (T)tv.inv_order;
 
     auto load_record = [&](Record<BASIS, ORDER, T>& r, int leaf) {
-        AI_CHECK(leaf >= 0 && leaf < tv.n_leaves);
+        AI_CHECK(leaf >= 0 && leaf < (MODE == kSelect ? tv.n_leaves : tv.n_records));
         if constexpr (MODE == kSelect) {
 #pragma unroll
             for (int k = 0; k < Record<BASIS, ORDER, T>::N; ++k) r.v[k] = leaf ? sel.rec[1][k] : sel.rec[0][k];

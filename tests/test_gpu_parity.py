@@ -221,6 +221,32 @@ def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
     assert abs(sums[0] - sums[1]) <= 1e-12 * float(np.sum(np.abs(y_p[np.isfinite(x)].astype(np.float64))))
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_cell_indexed_records_give_identical_bits(name, monkeypatch):
+    """Rank-mode tables with at most 32 (16) coarse cells store one record per coarse cell; the
+    evaluation, reduction and multi-table kernels then address records by cell.  Same record
+    contents, so identical bits to the leaf-indexed layout (AI_B200_NO_CELL_RECORDS=1); the index
+    kernel still reports the LEAF."""
+    g = golden(name)
+    tab_c = dev_table(name)
+    if not tab_c.info()["cell_records"]:
+        pytest.skip("table does not use cell-indexed records")
+    assert tab_c.info()["lookup_mode"] == 2
+    monkeypatch.setenv("AI_B200_NO_CELL_RECORDS", "1")
+    tab_l = dev_table(name)
+    assert not tab_l.info()["cell_records"]
+    lo, hi = float(g.lower_bound), float(g.upper_bound)
+    x = np.concatenate([g.x, np.random.default_rng(10).uniform(lo, hi, 1 << 18).astype(g.dtype), np.sort(g.x)])
+    assert np.array_equal(gpu_eval(tab_c, x), gpu_eval(tab_l, x), equal_nan=True)
+    assert np.array_equal(gpu_index(tab_c, g.x), g.idx_ref)
+    for mode in (1, 2, 3):
+        monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
+        monkeypatch.delenv("AI_B200_NO_CELL_RECORDS", raising=False)
+        tab_m = dev_table(name)
+        assert np.array_equal(gpu_eval(tab_m, g.x), gpu_eval(tab_l, g.x), equal_nan=True)
+        assert np.array_equal(gpu_index(tab_m, g.x), g.idx_ref)
+
+
 def test_saved_tables_take_the_packed_header():
     """All 27 saved approximations are dyadic on [0, 20]: every one with more than two leaves
     qualifies; the deep config-4 trees (breakpoints with > 15 significant bits) do not."""
