@@ -140,7 +140,8 @@ struct GridPlan {
     int rank_mode = 0;
     unsigned div_mul = 0, div_shift = 0, div_add = 0;
     unsigned cont = 0;
-    std::vector<uint32_t> coarse_leaf;   // rank mode: leaf of every coarse cell
+    int coarse_ok = 0;                   // div_* map a fine cell to its coarse cell, coarse_leaf is valid
+    std::vector<uint32_t> coarse_leaf;   // leaf of every coarse cell
 };
 
 long long gcd_ll(long long a, long long b) {
@@ -148,8 +149,11 @@ long long gcd_ll(long long a, long long b) {
     return a < 0 ? -a : a;
 }
 
-// Try to express first[] as "rank of the coarse cell in a <= 64-bit bitmap".  Everything is
-// verified exhaustively over the G fine cells; on any mismatch rank mode stays off.
+// Coarse cells: when every breakpoint sits on a multiple of q fine cells (q = gcd of the breakpoint
+// offsets), coarse cell = fine cell / q by an exact multiply-shift.  Two uses, both verified
+// exhaustively over the G fine cells (on any mismatch they stay off):
+//   * records stored once per coarse cell (coarse_ok): the cell index addresses the record;
+//   * with <= 32 coarse cells, the leaf as the rank of the cell in a bitmap (rank_mode).
 void plan_rank(const std::vector<double>& b, GridPlan* gp) {
     if (gp->K != 0 || gp->p < 0) return;
     const int64_t L = (int64_t)b.size() - 1;
@@ -161,7 +165,7 @@ void plan_rank(const std::vector<double>& b, GridPlan* gp) {
     }
     if (q == 0) q = G;                                   // single leaf
     const long long Gc = (G + q - 1) / q;
-    if (Gc > 32) return;
+    if (Gc > 65536) return;
     unsigned mul = 0, sh = 0;
     bool found = false;
     for (int S = 31; S >= 0 && !found; --S) {
@@ -173,20 +177,28 @@ void plan_rank(const std::vector<double>& b, GridPlan* gp) {
         if (ok) { mul = (unsigned)M; sh = (unsigned)S; found = true; }
     }
     if (!found) return;
-    unsigned cont = 0;
-    for (long long c = 1; c < Gc; ++c)
-        if (gp->first[(size_t)(c * q)] == gp->first[(size_t)((c - 1) * q)]) cont |= (1u << c);
     const unsigned add = (unsigned)(0u - (unsigned)gp->g0 * mul);      // -g0 * mul  (mod 2^32)
+    std::vector<uint32_t> coarse_leaf((size_t)Gc);
+    for (long long c = 0; c < Gc; ++c) coarse_leaf[(size_t)c] = gp->first[(size_t)(c * q)];
     for (int g = 0; g < G; ++g) {                        // exhaustive check of the device formula
         const unsigned gabs = (unsigned)(gp->g0 + g);    // what Lookup::cell_abs returns
+        const unsigned c = (gabs * mul + add) >> sh;
+        if (c >= (unsigned)Gc || coarse_leaf[c] != gp->first[g]) return;
+    }
+    gp->coarse_ok = 1; gp->div_mul = mul; gp->div_shift = sh; gp->div_add = add;
+    gp->coarse_leaf.swap(coarse_leaf);
+    if (Gc > 32) return;
+    unsigned cont = 0;
+    for (long long c = 1; c < Gc; ++c)
+        if (gp->coarse_leaf[(size_t)c] == gp->coarse_leaf[(size_t)(c - 1)]) cont |= (1u << c);
+    for (int g = 0; g < G; ++g) {
+        const unsigned gabs = (unsigned)(gp->g0 + g);
         const unsigned c = (gabs * mul + add) >> sh;
         const unsigned below = (c >= 31) ? ~0u : ((2u << c) - 1u);
         const int leaf = (int)c - __builtin_popcount(cont & below);
         if (leaf != (int)gp->first[g]) return;
     }
-    gp->rank_mode = 1; gp->div_mul = mul; gp->div_shift = sh; gp->div_add = add; gp->cont = cont;
-    gp->coarse_leaf.resize((size_t)Gc);
-    for (long long c = 0; c < Gc; ++c) gp->coarse_leaf[(size_t)c] = gp->first[(size_t)(c * q)];
+    gp->rank_mode = 1; gp->cont = cont;
 }
 
 bool cells_for(const std::vector<double>& b, int p, long long* g0, long long* glast) {
@@ -333,16 +345,21 @@ HeaderPack<T> plan_header_pack(const ai_table* t) {
 
 template <typename T>
 int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector<unsigned char>* image,
-                const HeaderPack<T>* pack = nullptr) {
+                const HeaderPack<T>* pack = nullptr, bool want_cell = true) {
     const int n = t->order;
     const int64_t L = t->L;
     const bool packed = pack && pack->ok && !global_layout;
-    // Records once per COARSE CELL instead of once per leaf (rank_mode 2): the cell index the
-    // lookup computes anyway addresses the record and the rank is never formed.  Only while the
-    // cells, like the leaves, fit one per bank (32 / 16), so that gathers stay conflict-free.
+    // Records once per COARSE CELL instead of once per leaf: the cell index the lookup computes
+    // anyway addresses the record; neither the rank nor the first[] table is needed on the
+    // evaluation path.  Offered while it at most doubles the record array (near-uniform trees);
+    // the caller keeps it only if the gathers stay conflict-free (plan_table).
     const int64_t Gc = (int64_t)gp.coarse_leaf.size();
-    const bool cell_records = gp.rank_mode && Gc >= L && Gc <= (sizeof(T) == 4 ? 32 : 16)
-                              && !std::getenv("AI_B200_NO_CELL_RECORDS");
+    // Measured (A/B on one box, random points): up to 32 cells it replaces the bitmap rank and always
+    // pays (cfg2 93 -> 97% of HBM); beyond 32 cells it replaces the first[] load, which pays for
+    // fp64 tables (64-leaf o7 87 -> 94%, 128-leaf o6 84 -> 93%) but not for the HBM-bound fp32
+    // order-3 tables (62 / 69 / 44 leaves: 93.5 / 98.8 / 93 -> 89%), so fp32 keeps first[] there.
+    const bool cell_records = want_cell && gp.coarse_ok && Gc >= L && Gc <= std::max<int64_t>(2 * L, 32)
+                              && (Gc <= 32 || sizeof(T) == 8) && !std::getenv("AI_B200_NO_CELL_RECORDS");
     const int64_t NR = cell_records ? Gc : L;            // records stored
     const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T))
                                 : (packed ? ai::rec_stride_packed(n) : ai::rec_stride(t->basis, n));
@@ -446,18 +463,27 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     HeaderPack<float> hp32;
     HeaderPack<double> hp64;
     if (t->dtype == AI_DTYPE_F32) hp32 = plan_header_pack<float>(t); else hp64 = plan_header_pack<double>(t);
-    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32)
-                                    : build_image<double>(t, gp, false, &image, &hp64);
-    if (rc) return rc;
-    const bool go_global = (forced == ai::kGlobal) || ((size_t)t->view.image_bytes > smem_cap);
-    if (go_global) {
-        rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image) : build_image<double>(t, gp, true, &image);
-        if (rc) return rc;
-    }
-
-    // ---- table residency -------------------------------------------------------------------
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
     const int full_copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
+    int mode = ai::kSmem, copies = 1;
+    bool go_global = false;
+    // First with one record per coarse cell (when the grid allows it); kept only if the gathers
+    // stay conflict-free -- packed with one record per bank, or fully replicated.  Otherwise
+    // planned again with one record per leaf.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool want_cell = (attempt == 0);
+    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32, want_cell)
+                                    : build_image<double>(t, gp, false, &image, &hp64, want_cell);
+    if (rc) return rc;
+    go_global = (forced == ai::kGlobal) || ((size_t)t->view.image_bytes > smem_cap);
+    if (go_global) {
+        rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image, nullptr, false)
+                                        : build_image<double>(t, gp, true, &image, nullptr, false);
+        if (rc) return rc;
+    }
+    const int64_t NR = t->view.n_records;                // records a warp may have to tell apart
+
+    // ---- table residency -------------------------------------------------------------------
     // shared-memory bytes of the bank layouts with `cp` copies: [grid table][breaks x cp][records x cp]
     auto bank_layout = [&](int cp, int* soff_b, int* soff_r) -> size_t {
         const size_t ob = (size_t)t->view.off_breaks;
@@ -468,10 +494,10 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     };
     // leaves a warp can address without two of them sharing a bank (odd record stride)
     const int64_t conflict_free_leaves = full_copies;
-    int mode = ai::kSmem, copies = 1;
+    mode = ai::kSmem; copies = 1;
     if (go_global) {
         mode = ai::kGlobal;
-    } else if (L > conflict_free_leaves || forced == ai::kSmemBank || forced == ai::kSmemBankN) {
+    } else if (NR > conflict_free_leaves || forced == ai::kSmemBank || forced == ai::kSmemBankN) {
         if (bank_layout(full_copies, nullptr, nullptr) <= smem_cap && forced != ai::kSmemBankN) {
             mode = ai::kSmemBank; copies = full_copies;
         } else if (gp.K == 0 || forced == ai::kSmemBankN) {
@@ -482,6 +508,15 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         }
     }
     if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
+    if (!t->cell_records || mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves)) break;
+    }   // attempts
+    auto bank_layout = [&](int cp, int* soff_b, int* soff_r) -> size_t {
+        const size_t ob = (size_t)t->view.off_breaks;
+        const size_t orr = ob + (size_t)round_up16((size_t)t->view.n_breaks_elems * esz * cp);
+        if (soff_b) *soff_b = (int)ob;
+        if (soff_r) *soff_r = (int)orr;
+        return orr + (size_t)round_up16((size_t)t->view.n_records_elems * esz * cp);
+    };
     // two leaves: both records ride in the kernel parameters, element-wise select instead of a gather
     // (the image stays: the reduction and multi-table kernels read it)
     if (!go_global && ((L == 2 && forced < 0) || (L <= 2 && forced == ai::kSelect))) {
@@ -519,7 +554,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
-    t->view.rank_mode = gp.rank_mode ? (t->cell_records ? 2 : 1) : 0;
+    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0);
     t->view.div_mul = gp.div_mul;
     t->view.div_shift = gp.div_shift;
     t->view.div_add = gp.div_add;

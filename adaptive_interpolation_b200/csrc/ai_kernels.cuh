@@ -110,8 +110,8 @@ struct TableView {
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
     int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit, 0 -> 32-bit
-    int rank_mode;                 // 1: leaf = rank in cont_mask of the coarse cell (no table read);
-                                   // 2: as 1, and rec[] holds one record per COARSE CELL (n_records of them)
+    int rank_mode;                 // bit 0: leaf = rank in cont_mask of the coarse cell (no table read);
+                                   // bit 1: rec[] holds one record per COARSE CELL (n_records of them)
     int n_records;                 // records in rec[]: L, or the coarse cell count in rank_mode 2
     unsigned div_mul, div_shift;   // coarse cell = (fine cell * div_mul) >> div_shift  (exact / q)
     unsigned div_add;              // -g0 * div_mul (mod 2^32): folds the "- g0" into the multiply
@@ -216,12 +216,11 @@ template <typename T> struct Lookup {
     // fine cell divided by the odd factor q of the leaf width (exact multiply-shift, verified on
     // the host for every fine cell); the leaf is the number of leaf starts at or before it.
     __device__ __forceinline__ unsigned coarse_cell(T x) const {
-        const unsigned c = (cell_abs(x) * div_mul + div_add) >> div_shift;
-        AI_CHECK(c < 32u);
-        return c;
+        return (cell_abs(x) * div_mul + div_add) >> div_shift;
     }
     __device__ __forceinline__ int rank_guess(T x) const {
         const unsigned c = coarse_cell(x);
+        AI_CHECK(c < 32u);
         const unsigned above = 0xfffffffeu << c;                 // bits strictly above c
         const int i = (int)c - __popc(cont & ~above);
         AI_CHECK(i >= 0 && i <= lmax);
@@ -234,12 +233,17 @@ template <typename T> struct Lookup {
     // N dependent chains interleave (ILP).
     template <int N>
     __device__ __forceinline__ void leaves(const T (&x)[N], int (&i)[N]) const {
-        if (rank_mode == 2) {
+        if (rank_mode & 2) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = (int)coarse_cell(x[e]);
             return;
         }
-        if (rank_mode) {
+        true_leaves<N>(x, i);
+    }
+    // the LEAF ordinal (what the index kernel reports), whatever the record layout
+    template <int N>
+    __device__ __forceinline__ void true_leaves(const T (&x)[N], int (&i)[N]) const {
+        if (rank_mode & 1) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = rank_guess(x[e]);
             return;
@@ -283,8 +287,10 @@ template <typename T> struct Lookup {
     // as leaf(), but also reproduces the reference for NaN: every `mid > x` test is false, the
     // walk always goes right and ends on the last leaf (approximator.py:287-290).
     __device__ __forceinline__ int leaf_nan_exact(T x) const {
-        const int i = rank_mode ? rank_guess(x) : leaf(x);      // the LEAF, also when records are per cell
-        return (x != x) ? lmax : i;
+        T xs[1] = {x};
+        int is[1];
+        true_leaves<1>(xs, is);                                  // the LEAF, also when records are per cell
+        return (x != x) ? lmax : is[0];
     }
 };
 

@@ -223,15 +223,14 @@ def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
 
 @pytest.mark.parametrize("name", NAMES)
 def test_cell_indexed_records_give_identical_bits(name, monkeypatch):
-    """Rank-mode tables with at most 32 (16) coarse cells store one record per coarse cell; the
-    evaluation, reduction and multi-table kernels then address records by cell.  Same record
+    """Tables whose breakpoints sit on a coarse grid of at most 2 L cells store one record per coarse
+    cell; the evaluation, reduction and multi-table kernels then address records by cell.  Same record
     contents, so identical bits to the leaf-indexed layout (AI_B200_NO_CELL_RECORDS=1); the index
     kernel still reports the LEAF."""
     g = golden(name)
     tab_c = dev_table(name)
     if not tab_c.info()["cell_records"]:
         pytest.skip("table does not use cell-indexed records")
-    assert tab_c.info()["lookup_mode"] == 2
     monkeypatch.setenv("AI_B200_NO_CELL_RECORDS", "1")
     tab_l = dev_table(name)
     assert not tab_l.info()["cell_records"]
