@@ -248,30 +248,52 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
         }
         if (!found) return fail(AI_ERR_TABLE, "cannot build a lookup grid for domain [%g, %g]", b.front(), b.back());
     }
-    const int G = (int)(gl - g0 + 1);
-    out->p = p; out->G = G; out->g0 = g0;
-    out->first.assign(G, 0);
-    // A negative p scales DOWN and can underflow for denormal-range x; widen the search window
-    // by one cell to the left so the result stays exact regardless.
-    const int margin = (p < 0) ? 1 : 0;
-    int64_t maxspan = 0;
-    for (int g = 0; g < G; ++g) {
-        const double left = std::ldexp((double)(g0 + g - margin), -p);
-        const double right = std::ldexp((double)(g0 + g + 1), -p);
-        // leaf holding `left`: #{k: b[k] <= left} - 1, clamped
-        int64_t f = (std::upper_bound(b.begin(), b.end(), left) - b.begin()) - 1;
-        f = std::min<int64_t>(std::max<int64_t>(f, 0), L - 1);
-        // last leaf with a point < right
-        int64_t l = (std::lower_bound(b.begin(), b.end(), right) - b.begin()) - 1;
-        l = std::min<int64_t>(std::max<int64_t>(l, 0), L - 1);
-        if (g == G - 1) l = L - 1;
-        if (g == 0) f = 0;
-        out->first[g] = (uint32_t)f;
-        maxspan = std::max(maxspan, l - f);
-    }
+    // first[] and the search depth K of the grid with scale 2^pp covering cells [c0, c1]
+    auto fill = [&](int pp, long long c0, long long c1, std::vector<uint32_t>* first, int* Kout) {
+        const int G = (int)(c1 - c0 + 1);
+        first->assign(G, 0);
+        // A negative p scales DOWN and can underflow for denormal-range x; widen the search window
+        // by one cell to the left so the result stays exact regardless.
+        const int margin = (pp < 0) ? 1 : 0;
+        int64_t maxspan = 0;
+        for (int g = 0; g < G; ++g) {
+            const double left = std::ldexp((double)(c0 + g - margin), -pp);
+            const double right = std::ldexp((double)(c0 + g + 1), -pp);
+            // leaf holding `left`: #{k: b[k] <= left} - 1, clamped
+            int64_t f = (std::upper_bound(b.begin(), b.end(), left) - b.begin()) - 1;
+            f = std::min<int64_t>(std::max<int64_t>(f, 0), L - 1);
+            // last leaf with a point < right
+            int64_t l = (std::lower_bound(b.begin(), b.end(), right) - b.begin()) - 1;
+            l = std::min<int64_t>(std::max<int64_t>(l, 0), L - 1);
+            if (g == G - 1) l = L - 1;
+            if (g == 0) f = 0;
+            (*first)[g] = (uint32_t)f;
+            maxspan = std::max(maxspan, l - f);
+        }
+        int K = 0;
+        while ((1LL << K) - 1 < maxspan) ++K;
+        *Kout = K;
+    };
     int K = 0;
-    while ((1LL << K) - 1 < maxspan) ++K;
-    if (exact && K != 0) return fail(AI_ERR_TABLE, "internal: exact grid has span %lld", (long long)maxspan);
+    fill(p, g0, gl, &out->first, &K);
+    if (exact && K != 0) return fail(AI_ERR_TABLE, "internal: exact grid has span %lld", (long long)((1LL << K) - 1));
+    // When a search follows anyway, a grid of at most 128 byte entries (32 words: every lane of a
+    // warp reads a different bank or the same word) is read in ONE shared-memory wavefront, where
+    // random reads of the 4096-cell table cost about 4.5 (ncu, config 4).  Take the coarse grid if
+    // the extra search steps cost less than that (a step is 1 wavefront in fp32, 2 in fp64).
+    if (!exact && K > 0 && L <= 256 && (gl - g0 + 1) > 128 && !std::getenv("AI_B200_NO_COARSE_GRID")) {
+        long long c0 = 0, c1 = 0;
+        for (int q = p - 1; q >= -1000; --q) {
+            if (!fits(q, grid_budget(128), &c0, &c1)) continue;
+            std::vector<uint32_t> first2;
+            int K2 = 0;
+            fill(q, c0, c1, &first2, &K2);
+            const double step = (dtype == AI_DTYPE_F32) ? 1.0 : 2.0;
+            if (K2 * step + 1.0 < K * step + 4.5) { p = q; g0 = c0; gl = c1; K = K2; out->first.swap(first2); }
+            break;
+        }
+    }
+    out->p = p; out->G = (int)(gl - g0 + 1); out->g0 = g0;
     out->K = K;
     if (!std::getenv("AI_B200_NO_RANK")) plan_rank(b, out);     // (env: test hook for the table path)
     return AI_OK;

@@ -16,7 +16,8 @@ GPU (ai_table_create).  The `gen_*` functions therefore return a short descripti
 selected kernel; it is stored in approx.code exactly where the reference stores its source text.
 
 x may be a numpy array (copied to the device and back OUTSIDE the timed region, as
-generate.py:481-489 does) or a torch CUDA tensor (used in place; a CUDA tensor is returned).
+generate.py:481-489 does), a torch CUDA tensor or any object with `__cuda_array_interface__`
+(cupy, numba, pycuda: used in place without a copy; a torch CUDA tensor is returned).
 No CUDA handles are ever stored on the Approximator, so write_to_file keeps working
 (checkpoint row).
 """
@@ -155,6 +156,8 @@ def _as_device(torch, x, dtype, device):
     """-> (x_dev tensor, was_numpy).  dtype is the TABLE dtype: the reference kernel is declared
     in it (generate.py:172-174) and feeding another dtype there is undefined; we convert."""
     tdt = torch.float32 if dtype == np.float32 else torch.float64
+    if not isinstance(x, torch.Tensor) and hasattr(x, "__cuda_array_interface__"):
+        x = torch.as_tensor(x, device=device)       # cupy / numba / pycuda arrays: zero-copy view
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
             return x.to(device=device, dtype=tdt).contiguous().view(-1), False

@@ -247,6 +247,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NCCL may print to stdout (e.g. its version banner under NCCL_DEBUG=VERSION); the contract is
+    # ONE JSON line there, so everything before that line goes to stderr at the descriptor level
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -388,6 +393,9 @@ def main():
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    os.close(stdout_fd)
     if rank != 0:
         return
     line = {

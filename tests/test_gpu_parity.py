@@ -805,3 +805,20 @@ def test_run_many_matches_run():
         generate.run_many(x, [])
     with pytest.raises(Exception):
         generate.run_many(x, [aps[0], golden("approx__64o6-p1.19209289551e-06")])
+
+
+def test_run_accepts_cuda_array_interface_objects():
+    """Device arrays of other libraries (cupy, numba, pycuda ...) are taken through
+    __cuda_array_interface__ without a copy; the result comes back as a torch CUDA tensor."""
+    class Foreign(object):                       # stands in for a cupy.ndarray
+        def __init__(self, t):
+            self._keep = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+    ap = golden("approx__32o6-p1.19209289551e-06")
+    x = np.random.default_rng(6).uniform(0, 20, 50001).astype(np.float32)
+    xd = to_dev(x)
+    y = generate.run(Foreign(xd), ap)
+    assert isinstance(y, torch.Tensor) and y.is_cuda
+    assert np.array_equal(y.cpu().numpy(), generate.run(x, ap))
+    seconds, y2 = generate.run_single(Foreign(xd), ap)
+    assert seconds > 0 and np.array_equal(y2.cpu().numpy(), y.cpu().numpy())
