@@ -505,7 +505,20 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
     return v;
 }
 #endif
-template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
+#ifndef AI_ST_MODE
+#define AI_ST_MODE 0               // 0: st.global.cs (evict-first), 1: plain st.global, 2: st.global.wt, 3: st.global.cg
+#endif
+template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) {
+#if AI_ST_MODE == 0
+    __stcs(p, v);
+#elif AI_ST_MODE == 1
+    *p = v;
+#elif AI_ST_MODE == 2
+    __stwt(p, v);
+#else
+    __stcg(p, v);
+#endif
+}
 
 // Make the table addressable for this CTA and return its base.  kSmem: copy the packed image
 // (16-byte chunks, whole CTA).  kSmemBank: copy grid table + breakpoints, then write every record
