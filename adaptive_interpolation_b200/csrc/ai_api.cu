@@ -121,6 +121,7 @@ struct ai_table {
     int copies = 1;                    // bank modes: copies per element
     int packed = 0;                    // 1: records carry the one-element header (modes kSmemP / kSmemBankP)
     int cell_records = 0;              // 1: one record per coarse cell (view.rank_mode 2)
+    int uniform_hdr = 0;               // 1: records carry no header, computed from the cell (modes kSmemU / kSmemBankU)
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
@@ -365,12 +366,38 @@ HeaderPack<T> plan_header_pack(const ai_table* t) {
     return hp;
 }
 
+// The computed record header of modes kSmemU / kSmemBankU: fp64 tables with one leaf per coarse
+// cell whose stored header is reproduced exactly by a_c = fma(c, w, lb) and one constant s.
+struct UniformHeader {
+    bool ok = false;
+    double w = 0, lb = 0, s = 0;
+};
+
+UniformHeader plan_uniform_header(const ai_table* t, const GridPlan& gp) {
+    UniformHeader u;
+    const int64_t L = t->L;
+    if (t->dtype != AI_DTYPE_F64 || t->basis == ai::kMono || !gp.coarse_ok || L <= 2 ||
+        (int64_t)gp.coarse_leaf.size() != L || std::getenv("AI_B200_NO_UNIFORM_HDR"))
+        return u;
+    u.lb = t->breaks[0];
+    u.w = t->breaks[1] - t->breaks[0];
+    u.s = 2.0 / (t->breaks[1] - t->breaks[0]);
+    for (int64_t c = 0; c < L; ++c) {
+        if (gp.coarse_leaf[(size_t)c] != (uint32_t)c) return u;
+        const double a = t->breaks[c], b = t->breaks[c + 1];
+        if (std::fma((double)c, u.w, u.lb) != a || 2.0 / (b - a) != u.s) return u;     // bit for bit
+    }
+    u.ok = true;
+    return u;
+}
+
 template <typename T>
 int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector<unsigned char>* image,
-                const HeaderPack<T>* pack = nullptr, bool want_cell = true) {
+                const HeaderPack<T>* pack = nullptr, bool want_cell = true, const UniformHeader* uni = nullptr) {
     const int n = t->order;
     const int64_t L = t->L;
-    const bool packed = pack && pack->ok && !global_layout;
+    const bool uniform = uni && uni->ok && !global_layout && want_cell && sizeof(T) == 8;
+    const bool packed = pack && pack->ok && !global_layout && !uniform;
     // Records once per COARSE CELL instead of once per leaf: the cell index the lookup computes
     // anyway addresses the record; neither the rank nor the first[] table is needed on the
     // evaluation path.  Offered while it at most doubles the record array (near-uniform trees);
@@ -384,8 +411,9 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
                               && (Gc <= 32 || sizeof(T) == 8) && !std::getenv("AI_B200_NO_CELL_RECORDS");
     const int64_t NR = cell_records ? Gc : L;            // records stored
     const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T))
-                                : (packed ? ai::rec_stride_packed(n) : ai::rec_stride(t->basis, n));
-    const int hdr = (t->basis == ai::kMono) ? 0 : (packed ? 1 : 2);
+                                : (uniform ? ai::rec_stride(ai::kMono, n)
+                                           : (packed ? ai::rec_stride_packed(n) : ai::rec_stride(t->basis, n)));
+    const int hdr = (t->basis == ai::kMono || uniform) ? 0 : (packed ? 1 : 2);
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
     const int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
@@ -420,6 +448,10 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     }
     t->rstride = R;
     t->packed = packed ? 1 : 0;
+    t->uniform_hdr = uniform ? 1 : 0;
+    t->view.u_w = uniform ? uni->w : 0.0;
+    t->view.u_lb = uniform ? uni->lb : 0.0;
+    t->view.u_s = uniform ? uni->s : 0.0;
     t->view.s0_hi = packed ? pack->s0_hi : 0;
     t->view.s0_lo = packed ? pack->s0_lo : 0;
     t->view.image_bytes = (int)total;
@@ -485,6 +517,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     HeaderPack<float> hp32;
     HeaderPack<double> hp64;
     if (t->dtype == AI_DTYPE_F32) hp32 = plan_header_pack<float>(t); else hp64 = plan_header_pack<double>(t);
+    const UniformHeader uni = plan_uniform_header(t, gp);
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
     const int full_copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
     int mode = ai::kSmem, copies = 1;
@@ -494,8 +527,8 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     // planned again with one record per leaf.
     for (int attempt = 0; attempt < 2; ++attempt) {
     const bool want_cell = (attempt == 0);
-    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32, want_cell)
-                                    : build_image<double>(t, gp, false, &image, &hp64, want_cell);
+    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32, want_cell, &uni)
+                                    : build_image<double>(t, gp, false, &image, &hp64, want_cell, &uni);
     if (rc) return rc;
     go_global = (forced == ai::kGlobal) || ((size_t)t->view.image_bytes > smem_cap);
     if (go_global) {
@@ -530,7 +563,9 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         }
     }
     if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
-    if (!t->cell_records || mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves)) break;
+    const bool layout_ok = !t->cell_records || mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves);
+    const bool header_ok = !t->uniform_hdr || mode == ai::kSmem || mode == ai::kSmemBank;   // only these have U kernels
+    if (layout_ok && header_ok) break;
     }   // attempts
     auto bank_layout = [&](int cp, int* soff_b, int* soff_r) -> size_t {
         const size_t ob = (size_t)t->view.off_breaks;
@@ -563,12 +598,14 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     }
     if (t->packed && mode == ai::kSmem) mode = ai::kSmemP;
     if (t->packed && mode == ai::kSmemBank) mode = ai::kSmemBankP;
+    if (t->uniform_hdr && mode == ai::kSmem) mode = ai::kSmemU;
+    if (t->uniform_hdr && mode == ai::kSmemBank) mode = ai::kSmemBankU;
     t->mode = mode;
     t->copies = copies;
     t->view.copies = copies;
     t->smem_resident = (mode != ai::kGlobal);
     t->eval_smem = 0;
-    if (mode == ai::kSmem || mode == ai::kSmemP) t->eval_smem = t->view.image_bytes;
+    if (mode == ai::kSmem || mode == ai::kSmemP || mode == ai::kSmemU) t->eval_smem = t->view.image_bytes;
     if (ai::mode_bank(mode))
         t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
     t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
@@ -615,7 +652,8 @@ int finish_table(ai_table* t) {
     if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->eval_smem);
     if (t->mode != ai::kGlobal && t->aux_smem > 48 * 1024) {
         int dummy = 0;      // opt the reduction kernel (packed layout) into large shared memory too
-        rc = prepare_dispatch(t->basis, t->dtype, t->order, t->packed ? ai::kSmemP : ai::kSmem, t->aux_smem, &dummy);
+        rc = prepare_dispatch(t->basis, t->dtype, t->order,
+                              t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem), t->aux_smem, &dummy);
         if (rc) return rc;
     }
     t->blocks_per_sm = bps;
@@ -724,7 +762,7 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     ai::MultiArgs args{};
     for (int j = 0; j < m && fuse; ++j) {
         const ai_table* t = tabs[j];
-        fuse = t->basis == t0->basis && t->order == t0->order && t->packed == t0->packed
+        fuse = t->basis == t0->basis && t->order == t0->order && t->packed == t0->packed && !t->uniform_hdr
                && (t->mode == ai::kSmem || t->mode == ai::kSmemP || t->mode == ai::kSelect)
                && (reinterpret_cast<uintptr_t>(y[j]) % 16) == (ax % 16);
         args.tv[j] = t->view;
@@ -811,7 +849,8 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     cfg.stream = s;
     cfg.select = nullptr;
     cudaError_t e;
-    const int m = (t->mode == ai::kGlobal) ? ai::kGlobal : (t->packed ? ai::kSmemP : ai::kSmem);
+    const int m = (t->mode == ai::kGlobal) ? ai::kGlobal
+                                           : (t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem));
     if constexpr (sizeof(T) == 4) {
         if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, m, cfg, t->view, x, result, n);
         else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, m, cfg, t->view, x, result, n);
@@ -1110,8 +1149,9 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->record_stride = t->rstride;
     info->image_bytes = t->view.image_bytes;
     info->smem_bytes = t->eval_smem;
-    info->residency = (t->mode == ai::kSmemP) ? ai::kSmem : (t->mode == ai::kSmemBankP ? ai::kSmemBank : t->mode);
-    info->header_packed = t->packed;
+    info->residency = (t->mode == ai::kSmemP || t->mode == ai::kSmemU) ? ai::kSmem
+                      : ((t->mode == ai::kSmemBankP || t->mode == ai::kSmemBankU) ? ai::kSmemBank : t->mode);
+    info->header_packed = t->uniform_hdr ? 2 : t->packed;
     info->cell_records = t->cell_records;
     info->bank_copies = t->copies;
     info->smem_resident = t->smem_resident;

@@ -58,7 +58,7 @@ struct Unit {
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
         cudaError_t e = raise_smem_limit(eval_kernel<BASIS, ORDER, T, MODE>, smem_bytes);
         if (e != cudaSuccess) return e;
-        if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kGlobal) {
+        if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kSmemU || MODE == kGlobal) {
             e = raise_smem_limit(eval_sum_kernel<BASIS, ORDER, T, MODE>, smem_bytes);
             if (e != cudaSuccess) return e;
         }
@@ -80,6 +80,10 @@ struct Switch {
             if constexpr (BASIS != kMono) {          // the monomial record has no header to pack
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::eval(a...);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::eval(a...);
+                if constexpr (sizeof(T) == 8) {      // computed header: fp64 tables only
+                    if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::eval(a...);
+                    if (mode == kSmemBankU) return Unit<BASIS, T, ORDER, kSmemBankU>::eval(a...);
+                }
             }
             return cudaErrorInvalidValue;
         }
@@ -91,6 +95,9 @@ struct Switch {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::sum(a...);
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::sum(a...);
+                if constexpr (sizeof(T) == 8) {
+                    if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::sum(a...);
+                }
             }
             return Unit<BASIS, T, ORDER, kSmem>::sum(a...);
         }
@@ -117,6 +124,10 @@ struct Switch {
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::prepare(smem_bytes, bps);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::prepare(smem_bytes, bps);
+                if constexpr (sizeof(T) == 8) {
+                    if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::prepare(smem_bytes, bps);
+                    if (mode == kSmemBankU) return Unit<BASIS, T, ORDER, kSmemBankU>::prepare(smem_bytes, bps);
+                }
             }
             return cudaErrorInvalidValue;
         }

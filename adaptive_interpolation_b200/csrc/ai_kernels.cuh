@@ -81,9 +81,19 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              integer instructions unpack.  One shared-memory wavefront less per 32 points on the
 //              return path that bounds random points (fp64: two less); the unpacked values are
 //              the stored ones bit for bit (verified per leaf on the host, else not packed).
-enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4, kSmemP = 5, kSmemBankP = 6 };
+//   kSmemU / kSmemBankU  (fp64 only) as kSmem / kSmemBank with NO record header at all: tables whose
+//              leaves all have one width (one leaf per coarse cell: the 8-leaf order-13 / order-7
+//              and the 64- / 128-leaf 2.2e-14 tables) have a_c = fma(c, w, lb) and one constant
+//              2/(b-a); the kernel computes both from the cell index (I2F + FMA) instead of
+//              gathering them: two more wavefronts off the return path.  Verified per cell on the
+//              host against the stored header, bit for bit.
+enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4, kSmemP = 5, kSmemBankP = 6,
+             kSmemU = 7, kSmemBankU = 8 };
 __host__ __device__ constexpr bool mode_packed_hdr(int mode) { return mode == kSmemP || mode == kSmemBankP; }
-__host__ __device__ constexpr bool mode_bank(int mode) { return mode == kSmemBank || mode == kSmemBankN || mode == kSmemBankP; }
+__host__ __device__ constexpr bool mode_uniform_hdr(int mode) { return mode == kSmemU || mode == kSmemBankU; }
+__host__ __device__ constexpr bool mode_bank(int mode) {
+    return mode == kSmemBank || mode == kSmemBankN || mode == kSmemBankP || mode == kSmemBankU;
+}
 constexpr int kMaxRecord = 16 + 1 + 2;         // AI_MAX_ORDER + 1 coefficients + [a, 2/(b-a)]
 // kSelect's table, passed by value as a kernel parameter; empty in every other mode
 template <typename T, int MODE> struct SelectTable {};
@@ -92,7 +102,8 @@ template <typename T> struct SelectTable<T, kSelect> {
     T rec[2][kMaxRecord];           // [a, 2/(b-a), c0..cn] ([c0..cn] for the monomial basis)
 };
 template <typename T, int MODE> struct Copies {
-    static constexpr int value = (MODE == kSmemBank || MODE == kSmemBankP) ? (sizeof(T) == 4 ? 32 : 16) : 1;
+    static constexpr int value =
+        (MODE == kSmemBank || MODE == kSmemBankP || MODE == kSmemBankU) ? (sizeof(T) == 4 ? 32 : 16) : 1;
 };
 
 // Everything a kernel needs to know about a table; passed by value (kernel parameter space).
@@ -120,6 +131,7 @@ struct TableView {
     double lo, hi;                 // g0 and g0+G-1 as floating point (exact in T)
     double inv_order;              // T(1./n) widened: the Legendre-like recurrence's divisor
     unsigned s0_hi, s0_lo;         // packed header: bits of S0 = max_i 2/(b_i-a_i) (fp32: s0_hi only)
+    double u_w, u_lb, u_s;         // computed header (kSmemU / kSmemBankU): a_c = fma(c, u_w, u_lb), 2/(b-a) = u_s
 };
 
 // ---------------------------------------------------------------------------------- helpers
@@ -143,7 +155,8 @@ __host__ __device__ constexpr int rec_stride_packed(int order) { return ((order 
 template <int BASIS, int ORDER, typename T, int MODE>
 __host__ __device__ constexpr int rec_stride_for() {
     return MODE == kGlobal ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
-                           : (mode_packed_hdr(MODE) ? rec_stride_packed(ORDER) : rec_stride(BASIS, ORDER));
+                           : (mode_packed_hdr(MODE) ? rec_stride_packed(ORDER)
+                                                    : (mode_uniform_hdr(MODE) ? rec_stride(kMono, ORDER) : rec_stride(BASIS, ORDER)));
 }
 
 __device__ __forceinline__ float  fma_(float a, float b, float c)    { return __fmaf_rn(a, b, c); }
@@ -318,6 +331,15 @@ template <int BASIS, int ORDER, typename T> struct Record {
 #pragma unroll
         for (int k = 0; k <= ORDER; ++k) v[2 + k] = rec[(1 + k) * STRIDE];
         unpack_header(w, s0_hi, s0_lo);
+    }
+    // computed header: rec = [c0..cn]; a and 2/(b-a) from the cell index
+    template <int STRIDE = 1>
+    __device__ __forceinline__ void load_uniform(const T* __restrict__ rec, int cell, T w, T lb, T s) {
+        static_assert(HDR == 2, "the monomial basis has no header");
+#pragma unroll
+        for (int k = 0; k <= ORDER; ++k) v[2 + k] = rec[k * STRIDE];
+        v[0] = fma_((T)cell, w, lb);
+        v[1] = s;
     }
     // run-time element stride (kSmemBankN)
     __device__ __forceinline__ void load_packed_strided(const T* __restrict__ rec, int stride, unsigned s0_hi,
@@ -527,7 +549,7 @@ template <typename T, int MODE>
 __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
     if constexpr (MODE == kGlobal || MODE == kSelect) {
         return tv.image;
-    } else if constexpr (MODE == kSmem || MODE == kSmemP) {
+    } else if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kSmemU) {
         const int4* src = reinterpret_cast<const int4*>(tv.image);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int k = threadIdx.x; k < tv.image_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
@@ -587,6 +609,8 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
             const T* p = records + leaf * R;
             if constexpr (VEC) r.load_vec(p);
             else if constexpr (PK) r.template load_packed<Copies<T, MODE>::value>(p, tv.s0_hi, tv.s0_lo);
+            else if constexpr (mode_uniform_hdr(MODE))
+                r.template load_uniform<Copies<T, MODE>::value>(p, leaf, (T)tv.u_w, (T)tv.u_lb, (T)tv.u_s);
             else if constexpr (MODE == kSmemBank) r.template load<Copies<T, kSmemBank>::value>(p);
             else if constexpr (MODE == kSmemBankN) {
                 // partial replication serves packed and unpacked headers (warp-uniform branch);
@@ -912,7 +936,8 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
-    static_assert(MODE == kSmem || MODE == kSmemP || MODE == kGlobal, "the reduction variant uses the packed layouts only");
+    static_assert(MODE == kSmem || MODE == kSmemP || MODE == kSmemU || MODE == kGlobal,
+                  "the reduction variant uses the packed layouts only");
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned char* base = table_base<T, MODE>(tv, smem);
     Lookup<T> lk;
@@ -927,7 +952,13 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
     for (long long k = gtid; k < n; k += gstride) {
         const T xv = __ldcs(x + k);
         const int i = lk.leaf(xv);
-        acc += (double)eval_leaf<BASIS, ORDER, T, 1, false, PK>(records + i * R, xv, inv_order, tv.s0_hi, tv.s0_lo);
+        if constexpr (mode_uniform_hdr(MODE)) {
+            Record<BASIS, ORDER, T> r;
+            r.template load_uniform<1>(records + i * R, i, (T)tv.u_w, (T)tv.u_lb, (T)tv.u_s);
+            acc += (double)eval_record<BASIS, ORDER, T>(r, xv, inv_order);
+        } else {
+            acc += (double)eval_leaf<BASIS, ORDER, T, 1, false, PK>(records + i * R, xv, inv_order, tv.s0_hi, tv.s0_lo);
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

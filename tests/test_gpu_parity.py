@@ -187,10 +187,11 @@ def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("mode", [0, 1, 3])
 def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
-    """Dyadic tables carry [a, 2/(b-a)] as one word (a's bits | exponent offset); the two integer
-    instructions that unpack it must reproduce the stored header exactly, so values are the same
-    bits as with the two-element header (AI_B200_NO_PACKED_HDR=1), in both shared-memory layouts,
-    for the evaluation, the reduction and the multi-table kernels."""
+    """Dyadic tables carry [a, 2/(b-a)] as one word (a's bits | exponent offset), fp64 tables with
+    one leaf width carry no header at all (a = fma(cell, w, lb)); what the kernel unpacks / computes
+    must reproduce the stored header exactly, so values are the same bits as with the two-element
+    header (AI_B200_NO_PACKED_HDR=1, AI_B200_NO_UNIFORM_HDR=1), in every shared-memory layout, for
+    the evaluation and the reduction kernels."""
     g = golden(name)
     monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
     tab_p = dev_table(name)
@@ -199,9 +200,15 @@ def test_packed_record_header_gives_identical_bits(name, mode, monkeypatch):
         pytest.skip("table does not qualify for the packed header")
     assert info_p["residency"] in (0, 1, 3, 4)
     monkeypatch.setenv("AI_B200_NO_PACKED_HDR", "1")
+    monkeypatch.setenv("AI_B200_NO_UNIFORM_HDR", "1")
     tab_u = dev_table(name)
     info_u = tab_u.info()
     assert not info_u["header_packed"]
+    if info_p["header_packed"] == 2:             # computed header: also against the one-word form
+        monkeypatch.delenv("AI_B200_NO_PACKED_HDR")
+        tab_1 = dev_table(name)
+        assert tab_1.info()["header_packed"] == 1
+        assert np.array_equal(gpu_eval(tab_1, g.x), gpu_eval(tab_u, g.x), equal_nan=True)
     assert info_u["residency"] == info_p["residency"] or mode == 1      # 32 (16) unpacked copies may not fit
     assert info_p["record_stride"] <= info_u["record_stride"]
     lo, hi = float(g.lower_bound), float(g.upper_bound)
@@ -251,8 +258,10 @@ def test_saved_tables_take_the_packed_header():
     qualifies; the deep config-4 trees (breakpoints with > 15 significant bits) do not."""
     for name in SAVED:
         info = dev_table(name).info()
-        assert info["header_packed"] == 1, (name, info)
-    assert dev_table("gen__cfg3_j0_cheb_o13_f64").info()["header_packed"] == 1
+        assert info["header_packed"] in (1, 2), (name, info)
+    assert dev_table("gen__cfg3_j0_cheb_o13_f64").info()["header_packed"] == 2       # 8 equal leaves
+    assert dev_table("approx__64o7-p2.22044604925e-14").info()["header_packed"] == 2  # 64 equal leaves
+    assert dev_table("approx__64o6-p1.19209289551e-06").info()["header_packed"] == 1
     assert dev_table("gen__cfg4_f1_leg_o7_f32").info()["header_packed"] == 0
 
 
@@ -724,7 +733,8 @@ MULTI_GROUPS = [
       "approx__ci32o6-p1.19209289551e-06", "approx__32o6-p1.19209289551e-06"], True),
     (["approx__64o6-p1.19209289551e-06", "approximations__64o6-p1.19209289551e-06",
       "approx__ci64o6-p1.19209289551e-06"], True),
-    (["gen__cfg3_j0_cheb_o13_f64", "approx__64o13-p1.19209289551e-06"], True),       # 8 leaves + select-mode table
+    (["gen__cfg3_j0_cheb_o13_f64", "approx__64o13-p1.19209289551e-06"], False),      # computed-header table: per-table launches
+    (["approx__64o13-p1.19209289551e-06", "approx__ci64o13-p1.19209289551e-06"], True),  # two select-mode tables
     (["approx__32o13-p1.19209289551e-06", "approx__ci32o13-p1.19209289551e-06"], True),
     (["gen__j0_leg_o7_f32", "gen__cfg4_f1_leg_o7_f32"], False),                      # 99 leaves: bank mode
     (["approx__32o6-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06"], False),  # orders differ

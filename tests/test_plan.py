@@ -38,7 +38,7 @@ def test_plan_is_consistent(name):
         assert info["bank_copies"] >= 2 and f.n_leaves > (32 if f.dtype == np.float32 else 16)
     if info["lookup_mode"] == 2:                       # in-register bitmap rank
         assert info["search_steps"] == 0
-    hdr = 0 if f.basis == "monomial" else (1 if info["header_packed"] else 2)
+    hdr = 0 if f.basis == "monomial" else {0: 2, 1: 1, 2: 0}[info["header_packed"]]
     assert info["record_stride"] >= f.order + 1 + hdr
 
 
@@ -47,7 +47,7 @@ def test_saved_tables_plan():
     for name in SAVED:
         info = plan(name)
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["header_packed"] == 1 and info["image_bytes"] <= 48 * 1024, (name, info)
+        assert info["header_packed"] in (1, 2) and info["image_bytes"] <= 48 * 1024, (name, info)
     assert plan("approx__32o6-p1.19209289551e-06")["lookup_mode"] == 2          # BASELINE configs[1]
     assert plan("approx__32o6-p1.19209289551e-06")["residency"] == 0
     assert plan("approx__32o3-p1.19209289551e-06")["residency"] == 1            # 62 leaves > 32 banks
@@ -58,7 +58,7 @@ def test_saved_tables_plan():
 
 def test_config_tables_plan():
     cfg3 = plan("gen__cfg3_j0_cheb_o13_f64")
-    assert cfg3["lookup_mode"] == 2 and cfg3["header_packed"] == 1 and cfg3["residency"] == 0
+    assert cfg3["lookup_mode"] == 2 and cfg3["header_packed"] == 2 and cfg3["residency"] == 0   # 8 equal leaves
     for name, k in (("gen__cfg4_f1_leg_o7_f32", 4), ("gen__cfg4_f1_leg_o7_f64", 6)):
         info = plan(name)                               # deep skewed trees: grid + bounded search
         assert info["search_steps"] == k and info["lookup_mode"] == 1 and info["header_packed"] == 0
@@ -76,6 +76,9 @@ def test_hooks(monkeypatch):
     monkeypatch.setenv("AI_B200_NO_PACKED_HDR", "1")
     assert plan(name)["header_packed"] == 0
     monkeypatch.delenv("AI_B200_NO_PACKED_HDR")
+    monkeypatch.setenv("AI_B200_NO_UNIFORM_HDR", "1")
+    assert plan("gen__cfg3_j0_cheb_o13_f64")["header_packed"] == 1
+    monkeypatch.delenv("AI_B200_NO_UNIFORM_HDR")
     monkeypatch.setenv("AI_B200_NO_RANK", "1")
     assert plan(name)["lookup_mode"] == 0
     monkeypatch.delenv("AI_B200_NO_RANK")
