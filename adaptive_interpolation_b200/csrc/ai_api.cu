@@ -373,20 +373,22 @@ struct UniformHeader {
     double w = 0, lb = 0, s = 0;
 };
 
+template <typename T>
 UniformHeader plan_uniform_header(const ai_table* t, const GridPlan& gp) {
     UniformHeader u;
     const int64_t L = t->L;
-    if (t->dtype != AI_DTYPE_F64 || t->basis == ai::kMono || !gp.coarse_ok || L <= 2 ||
-        (int64_t)gp.coarse_leaf.size() != L || std::getenv("AI_B200_NO_UNIFORM_HDR"))
+    // fp32: only while the table stays packed (<= 32 cells); its bank-mode tables keep first[] + header
+    if (t->basis == ai::kMono || !gp.coarse_ok || L <= 2 || (int64_t)gp.coarse_leaf.size() != L ||
+        (sizeof(T) == 4 && L > 32) || std::getenv("AI_B200_NO_UNIFORM_HDR"))
         return u;
-    u.lb = t->breaks[0];
-    u.w = t->breaks[1] - t->breaks[0];
-    u.s = 2.0 / (t->breaks[1] - t->breaks[0]);
+    const T lb = (T)t->breaks[0], w = (T)t->breaks[1] - (T)t->breaks[0];
+    const T s = (T)2 / ((T)t->breaks[1] - (T)t->breaks[0]);
     for (int64_t c = 0; c < L; ++c) {
         if (gp.coarse_leaf[(size_t)c] != (uint32_t)c) return u;
-        const double a = t->breaks[c], b = t->breaks[c + 1];
-        if (std::fma((double)c, u.w, u.lb) != a || 2.0 / (b - a) != u.s) return u;     // bit for bit
+        const T a = (T)t->breaks[c], b = (T)t->breaks[c + 1];
+        if (std::fma((T)c, w, lb) != a || (T)2 / (b - a) != s) return u;     // bit for bit, in table arithmetic
     }
+    u.lb = lb; u.w = w; u.s = s;
     u.ok = true;
     return u;
 }
@@ -396,7 +398,7 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
                 const HeaderPack<T>* pack = nullptr, bool want_cell = true, const UniformHeader* uni = nullptr) {
     const int n = t->order;
     const int64_t L = t->L;
-    const bool uniform = uni && uni->ok && !global_layout && want_cell && sizeof(T) == 8;
+    const bool uniform = uni && uni->ok && !global_layout && want_cell;
     const bool packed = pack && pack->ok && !global_layout && !uniform;
     // Records once per COARSE CELL instead of once per leaf: the cell index the lookup computes
     // anyway addresses the record; neither the rank nor the first[] table is needed on the
@@ -517,7 +519,8 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     HeaderPack<float> hp32;
     HeaderPack<double> hp64;
     if (t->dtype == AI_DTYPE_F32) hp32 = plan_header_pack<float>(t); else hp64 = plan_header_pack<double>(t);
-    const UniformHeader uni = plan_uniform_header(t, gp);
+    const UniformHeader uni = (t->dtype == AI_DTYPE_F32) ? plan_uniform_header<float>(t, gp)
+                                                         : plan_uniform_header<double>(t, gp);
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
     const int full_copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
     int mode = ai::kSmem, copies = 1;
@@ -564,7 +567,8 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     }
     if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
     const bool layout_ok = !t->cell_records || mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves);
-    const bool header_ok = !t->uniform_hdr || mode == ai::kSmem || mode == ai::kSmemBank;   // only these have U kernels
+    // only these have computed-header kernels (the bank form for fp64 only)
+    const bool header_ok = !t->uniform_hdr || mode == ai::kSmem || (mode == ai::kSmemBank && t->dtype == AI_DTYPE_F64);
     if (layout_ok && header_ok) break;
     }   // attempts
     auto bank_layout = [&](int cp, int* soff_b, int* soff_r) -> size_t {

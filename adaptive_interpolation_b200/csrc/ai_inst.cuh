@@ -80,8 +80,8 @@ struct Switch {
             if constexpr (BASIS != kMono) {          // the monomial record has no header to pack
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::eval(a...);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::eval(a...);
-                if constexpr (sizeof(T) == 8) {      // computed header: fp64 tables only
-                    if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::eval(a...);
+                if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::eval(a...);
+                if constexpr (sizeof(T) == 8) {      // fp32 tables beyond 32 cells keep first[] + header
                     if (mode == kSmemBankU) return Unit<BASIS, T, ORDER, kSmemBankU>::eval(a...);
                 }
             }
@@ -95,9 +95,7 @@ struct Switch {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::sum(a...);
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::sum(a...);
-                if constexpr (sizeof(T) == 8) {
-                    if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::sum(a...);
-                }
+                if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::sum(a...);
             }
             return Unit<BASIS, T, ORDER, kSmem>::sum(a...);
         }
@@ -124,8 +122,8 @@ struct Switch {
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::prepare(smem_bytes, bps);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::prepare(smem_bytes, bps);
+                if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::prepare(smem_bytes, bps);
                 if constexpr (sizeof(T) == 8) {
-                    if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::prepare(smem_bytes, bps);
                     if (mode == kSmemBankU) return Unit<BASIS, T, ORDER, kSmemBankU>::prepare(smem_bytes, bps);
                 }
             }

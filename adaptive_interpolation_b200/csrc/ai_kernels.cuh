@@ -81,7 +81,7 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              integer instructions unpack.  One shared-memory wavefront less per 32 points on the
 //              return path that bounds random points (fp64: two less); the unpacked values are
 //              the stored ones bit for bit (verified per leaf on the host, else not packed).
-//   kSmemU / kSmemBankU  (fp64 only) as kSmem / kSmemBank with NO record header at all: tables whose
+//   kSmemU / kSmemBankU  (the bank form for fp64 only) as kSmem / kSmemBank with NO record header at all: tables whose
 //              leaves all have one width (one leaf per coarse cell: the 8-leaf order-13 / order-7
 //              and the 64- / 128-leaf 2.2e-14 tables) have a_c = fma(c, w, lb) and one constant
 //              2/(b-a); the kernel computes both from the cell index (I2F + FMA) instead of
