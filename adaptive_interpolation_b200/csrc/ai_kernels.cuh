@@ -601,7 +601,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     const T inv_order = (T)tv.inv_order;
 
     auto load_record = [&](Record<BASIS, ORDER, T>& r, int leaf) {
-        AI_CHECK(leaf >= 0 && leaf < (MODE == kSelect ? tv.n_leaves : tv.n_records));
+        AI_CHECK(leaf >= 0 && leaf < (MODE == kSelect ? 2 : tv.n_records));   // kSelect: rec[1] == rec[0] for one leaf
         if constexpr (MODE == kSelect) {
 #pragma unroll
             for (int k = 0; k < Record<BASIS, ORDER, T>::N; ++k) r.v[k] = leaf ? sel.rec[1][k] : sel.rec[0][k];

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 TABLES = ["approx__32o6-p1.19209289551e-06", "approx__32o3-p1.19209289551e-06", "gen__cfg4_f1_leg_o7_f32",
           "gen__cfg4_f1_leg_o7_f64", "approximations__64o5-p2.22044604925e-14", "gen__j0_mono_o13_f64",
-          "gen__cfg3_j0_cheb_o13_f64", "gen__line1_mono_o1_f64"]
+          "gen__cfg3_j0_cheb_o13_f64", "gen__line1_mono_o1_f64", "approx__64o13-p1.19209289551e-06",
+          "approx__64o7-p2.22044604925e-14", "approx__32o7-p1.19209289551e-06"]
 
 
 def child():
@@ -33,6 +34,11 @@ def child():
             tab.sum_ptr(xd.data_ptr(), res.data_ptr(), n, None)
             torch.cuda.synchronize()
         tab.eval_host(x)
+        # several tables over the same x (fused when the layout allows it, else per-table launches)
+        xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        y0, y1 = torch.empty_like(xd), torch.empty_like(xd)
+        tables.DeviceTable.eval_multi_ptr([tab, tab], xd.data_ptr(), [y0.data_ptr(), y1.data_ptr()], xd.numel(), None)
+        torch.cuda.synchronize()
         print(name, "mode", os.environ.get("AI_B200_FORCE_MODE", "auto"), "residency", info["residency"],
               "lookup", info["lookup_mode"], "ok", flush=True)
 
@@ -41,9 +47,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for mode in (None, "0", "1", "2", "3"):
+        for mode in (None, "0", "1", "2", "3", "4", "nohdr", "nocell"):
             env = dict(os.environ)
-            if mode is not None:
+            if mode == "nohdr":
+                env["AI_B200_NO_PACKED_HDR"] = env["AI_B200_NO_UNIFORM_HDR"] = "1"
+            elif mode == "nocell":
+                env["AI_B200_NO_CELL_RECORDS"] = env["AI_B200_NO_UNIFORM_HDR"] = "1"
+            elif mode is not None:
                 env["AI_B200_FORCE_MODE"] = mode
             r = subprocess.run([sys.executable, __file__, "child"], env=env)
             if r.returncode != 0:
