@@ -766,8 +766,9 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     ai::MultiArgs args{};
     for (int j = 0; j < m && fuse; ++j) {
         const ai_table* t = tabs[j];
-        fuse = t->basis == t0->basis && t->order == t0->order && t->packed == t0->packed && !t->uniform_hdr
-               && (t->mode == ai::kSmem || t->mode == ai::kSmemP || t->mode == ai::kSelect)
+        fuse = t->basis == t0->basis && t->order == t0->order && t->packed == t0->packed
+               && t->uniform_hdr == t0->uniform_hdr
+               && (t->mode == ai::kSmem || t->mode == ai::kSmemP || t->mode == ai::kSmemU || t->mode == ai::kSelect)
                && (reinterpret_cast<uintptr_t>(y[j]) % 16) == (ax % 16);
         args.tv[j] = t->view;
         args.y[j] = y[j];
@@ -783,6 +784,7 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
         return AI_OK;
     }
     args.m = m;
+    const int hdr_form = t0->uniform_hdr ? 2 : t0->packed;
     constexpr int VN = ai::Vec<T>::N;
     long long head = (long long)(((16 - (ax % 16)) % 16) / sizeof(T));
     if (head > n) head = n;
@@ -796,13 +798,13 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     cfg.select = nullptr;
     cudaError_t e;
     if constexpr (sizeof(T) == 4) {
-        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f32(t0->order, t0->packed, cfg, args, x, n, head, nvec);
-        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f32(t0->order, t0->packed, cfg, args, x, n, head, nvec);
-        else e = ai::launch_multi_mono_f32(t0->order, t0->packed, cfg, args, x, n, head, nvec);
+        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f32(t0->order, hdr_form, cfg, args, x, n, head, nvec);
+        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f32(t0->order, hdr_form, cfg, args, x, n, head, nvec);
+        else e = ai::launch_multi_mono_f32(t0->order, hdr_form, cfg, args, x, n, head, nvec);
     } else {
-        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f64(t0->order, t0->packed, cfg, args, x, n, head, nvec);
-        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f64(t0->order, t0->packed, cfg, args, x, n, head, nvec);
-        else e = ai::launch_multi_mono_f64(t0->order, t0->packed, cfg, args, x, n, head, nvec);
+        if (t0->basis == ai::kCheb) e = ai::launch_multi_cheb_f64(t0->order, hdr_form, cfg, args, x, n, head, nvec);
+        else if (t0->basis == ai::kLeg) e = ai::launch_multi_leg_f64(t0->order, hdr_form, cfg, args, x, n, head, nvec);
+        else e = ai::launch_multi_mono_f64(t0->order, hdr_form, cfg, args, x, n, head, nvec);
     }
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "multi-table kernel launch failed: %s", cudaGetErrorString(e));
     if (fused_out) *fused_out = 1;

@@ -49,10 +49,10 @@ struct Unit {
     }
     static cudaError_t multi(const LaunchCfg& c, const MultiArgs& a, const T* x, long long n, long long head,
                              long long nvec) {
-        constexpr bool PK = mode_packed_hdr(MODE);
-        cudaError_t e = raise_smem_limit(eval_multi_kernel<BASIS, ORDER, T, PK>, c.smem_bytes);
+        constexpr int HM = mode_packed_hdr(MODE) ? 1 : (mode_uniform_hdr(MODE) ? 2 : 0);
+        cudaError_t e = raise_smem_limit(eval_multi_kernel<BASIS, ORDER, T, HM>, c.smem_bytes);
         if (e != cudaSuccess) return e;
-        eval_multi_kernel<BASIS, ORDER, T, PK><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(a, x, n, head, nvec);
+        eval_multi_kernel<BASIS, ORDER, T, HM><<<c.grid, kBlock, c.smem_bytes, c.stream>>>(a, x, n, head, nvec);
         return cudaGetLastError();
     }
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
@@ -104,8 +104,9 @@ struct Switch {
     }
     template <typename... A> static cudaError_t multi(int order, int packed, A&&... a) {
         if (order == ORDER) {
-            if constexpr (BASIS != kMono) {
-                if (packed) return Unit<BASIS, T, ORDER, kSmemP>::multi(a...);
+            if constexpr (BASIS != kMono) {          // packed: the tables' common header form (0, 1, 2)
+                if (packed == 1) return Unit<BASIS, T, ORDER, kSmemP>::multi(a...);
+                if (packed == 2) return Unit<BASIS, T, ORDER, kSmemU>::multi(a...);
             }
             return packed ? cudaErrorInvalidValue : Unit<BASIS, T, ORDER, kSmem>::multi(a...);
         }

@@ -795,7 +795,8 @@ struct MultiArgs {
     int m;
 };
 
-template <int BASIS, int ORDER, typename T, bool PK>
+// HM: record header form shared by the m tables -- 0 [a, 2/(b-a)], 1 one word, 2 computed
+template <int BASIS, int ORDER, typename T, int HM>
 __global__ void __launch_bounds__(kBlock, 1)
 eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ x,
                   long long n, long long head, long long nvec) {
@@ -813,11 +814,13 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
     constexpr int U = UnrollMulti<T>::value;
     constexpr long long kTile = (long long)kBlock * U;
     constexpr int NE = U * VN;
-    constexpr int R = PK ? rec_stride_packed(ORDER) : rec_stride(BASIS, ORDER);
+    constexpr int R = (HM == 1) ? rec_stride_packed(ORDER) : (HM == 2 ? rec_stride(kMono, ORDER) : rec_stride(BASIS, ORDER));
     const V* __restrict__ xv = reinterpret_cast<const V*>(x + head);
     const long long full_tiles = nvec / kTile;
-    auto load_rec = [&](Record<BASIS, ORDER, T>& r, const T* p, int j) {
-        if constexpr (PK) r.template load_packed<1>(p, args.tv[j].s0_hi, args.tv[j].s0_lo);
+    auto load_rec = [&](Record<BASIS, ORDER, T>& r, const T* records, int idx, int j) {
+        const T* p = records + idx * R;
+        if constexpr (HM == 1) r.template load_packed<1>(p, args.tv[j].s0_hi, args.tv[j].s0_lo);
+        else if constexpr (HM == 2) r.template load_uniform<1>(p, idx, (T)args.tv[j].u_w, (T)args.tv[j].u_lb, (T)args.tv[j].u_s);
         else r.template load<1>(p);
     };
 
@@ -831,7 +834,7 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
         lk.init(args.tv[j], smem + args.soff[j]);
         const T* records = reinterpret_cast<const T*>(smem + args.soff[j] + args.tv[j].off_records);
         Record<BASIS, ORDER, T> r;
-        load_rec(r, records + lk.leaf(xs) * R, j);
+        load_rec(r, records, lk.leaf(xs), j);
         return eval_record<BASIS, ORDER, T>(r, xs, (T)0);
     };
 
@@ -865,7 +868,7 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
             T ys[NE];
             if (uniform) {
                 Record<BASIS, ORDER, T> rec;
-                load_rec(rec, records + li[0] * R, j);
+                load_rec(rec, records, li[0], j);
                 if constexpr (sizeof(T) == 4 && AI_PACKED_F32) {
 #pragma unroll
                     for (int e = 0; e < NE; e += 2) {
@@ -881,8 +884,8 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 #pragma unroll
                     for (int e = 0; e < NE; e += 2) {
                         Record<BASIS, ORDER, T> ra, rb;
-                        load_rec(ra, records + li[e] * R, j);
-                        load_rec(rb, records + li[e + 1] * R, j);
+                        load_rec(ra, records, li[e], j);
+                        load_rec(rb, records, li[e + 1], j);
                         const float2 r2 = eval_record_pair<BASIS, ORDER>(ra, rb, xs[e], xs[e + 1]);
                         ys[e] = r2.x; ys[e + 1] = r2.y;
                     }
@@ -890,7 +893,7 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 #pragma unroll
                     for (int e = 0; e < NE; ++e) {
                         Record<BASIS, ORDER, T> rec;
-                        load_rec(rec, records + li[e] * R, j);
+                        load_rec(rec, records, li[e], j);
                         ys[e] = eval_record<BASIS, ORDER, T>(rec, xs[e], (T)0);
                     }
                 }

@@ -733,7 +733,10 @@ MULTI_GROUPS = [
       "approx__ci32o6-p1.19209289551e-06", "approx__32o6-p1.19209289551e-06"], True),
     (["approx__64o6-p1.19209289551e-06", "approximations__64o6-p1.19209289551e-06",
       "approx__ci64o6-p1.19209289551e-06"], True),
-    (["gen__cfg3_j0_cheb_o13_f64", "approx__64o13-p1.19209289551e-06"], False),      # computed-header table: per-table launches
+    (["gen__cfg3_j0_cheb_o13_f64", "approx__64o13-p1.19209289551e-06"], False),      # computed header + one-word header
+    (["gen__cfg3_j0_cheb_o13_f64", "gen__cfg3_j0_cheb_o13_f64"], True),              # two computed-header tables
+    (["approx__64o7-p1.19209289551e-06", "approx__ci64o7-p1.19209289551e-06"], True),
+    (["approx__32o7-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06"], True),
     (["approx__64o13-p1.19209289551e-06", "approx__ci64o13-p1.19209289551e-06"], True),  # two select-mode tables
     (["approx__32o13-p1.19209289551e-06", "approx__ci32o13-p1.19209289551e-06"], True),
     (["gen__j0_leg_o7_f32", "gen__cfg4_f1_leg_o7_f32"], False),                      # 99 leaves: bank mode
