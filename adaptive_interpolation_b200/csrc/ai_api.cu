@@ -166,7 +166,7 @@ void plan_rank(const std::vector<double>& b, GridPlan* gp) {
     }
     if (q == 0) q = G;                                   // single leaf
     const long long Gc = (G + q - 1) / q;
-    if (Gc > 65536) return;
+    if (Gc > (1 << 21)) return;
     unsigned mul = 0, sh = 0;
     bool found = false;
     for (int S = 31; S >= 0 && !found; --S) {
@@ -410,7 +410,7 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     // fp64 tables (64-leaf o7 87 -> 94%, 128-leaf o6 84 -> 93%) but not for the HBM-bound fp32
     // order-3 tables (62 / 69 / 44 leaves: 93.5 / 98.8 / 93 -> 89%), so fp32 keeps first[] there.
     const bool cell_records = want_cell && gp.coarse_ok && Gc >= L && Gc <= std::max<int64_t>(2 * L, 32)
-                              && (Gc <= 32 || sizeof(T) == 8) && !std::getenv("AI_B200_NO_CELL_RECORDS");
+                              && (Gc <= 32 || sizeof(T) == 8 || global_layout) && !std::getenv("AI_B200_NO_CELL_RECORDS");
     const int64_t NR = cell_records ? Gc : L;            // records stored
     const int R = global_layout ? ai::rec_stride_global(t->basis, n, (int)sizeof(T))
                                 : (uniform ? ai::rec_stride(ai::kMono, n)
@@ -528,6 +528,12 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     // First with one record per coarse cell (when the grid allows it); kept only if the gathers
     // stay conflict-free -- packed with one record per bank, or fully replicated.  Otherwise
     // planned again with one record per leaf.
+    // (does the one-record-per-leaf image fit in shared memory?  Then the cell layout must not push
+    // the table out to the global path just because it is up to twice as large.)
+    rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32, false, &uni)
+                                    : build_image<double>(t, gp, false, &image, &hp64, false, &uni);
+    if (rc) return rc;
+    const bool leaf_image_fits = (size_t)t->view.image_bytes <= smem_cap;
     for (int attempt = 0; attempt < 2; ++attempt) {
     const bool want_cell = (attempt == 0);
     rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32, want_cell, &uni)
@@ -535,8 +541,9 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     if (rc) return rc;
     go_global = (forced == ai::kGlobal) || ((size_t)t->view.image_bytes > smem_cap);
     if (go_global) {
-        rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image, nullptr, false)
-                                        : build_image<double>(t, gp, true, &image, nullptr, false);
+        // (cell-indexed records also here: the record gather then needs no first[] access before it)
+        rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image, nullptr, want_cell)
+                                        : build_image<double>(t, gp, true, &image, nullptr, want_cell);
         if (rc) return rc;
     }
     const int64_t NR = t->view.n_records;                // records a warp may have to tell apart
@@ -566,7 +573,10 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         }
     }
     if (!go_global && forced == ai::kSmem) { mode = ai::kSmem; copies = 1; }
-    const bool layout_ok = !t->cell_records || mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves);
+    // (NR == L: one leaf per cell, the cell layout costs nothing and is kept in every mode)
+    const bool layout_ok = !t->cell_records || NR == L ||
+                           (mode == ai::kGlobal && (!leaf_image_fits || forced == ai::kGlobal)) ||
+                           mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves);
     // only these have computed-header kernels (the bank form for fp64 only)
     const bool header_ok = !t->uniform_hdr || mode == ai::kSmem || (mode == ai::kSmemBank && t->dtype == AI_DTYPE_F64);
     if (layout_ok && header_ok) break;
