@@ -27,7 +27,7 @@ namespace ai {
 #define AI_MIN_BLOCKS 1            // __launch_bounds__ second argument (register cap)
 #endif
 #ifndef AI_PREFETCH
-#define AI_PREFETCH 1              // 1: load tile k+1 before evaluating tile k
+#define AI_PREFETCH 1              // 1: load tile k+1 before evaluating tile k; 2: tiles k+1 and k+2 in flight
 #endif
 #ifndef AI_UNIFORM_PATH
 #define AI_UNIFORM_PATH 2          // 0: off, 1: test every tile, 2: adaptive (re-probe every 16 tiles)
@@ -665,8 +665,16 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
 #if AI_PREFETCH
     if (tile < full_tiles) load_tile(in, tile);
 #endif
+#if AI_PREFETCH == 2
+    V nxt[kUnroll];                          // tile k+1, in flight since the previous iteration
+    if (tile + gridDim.x < full_tiles) load_tile(nxt, tile + gridDim.x);
+#endif
     for (; tile < full_tiles; tile += gridDim.x) {
-#if AI_PREFETCH
+#if AI_PREFETCH == 2
+        V nxt2[kUnroll];                     // tile k+2: two tiles in flight per thread
+        const long long next2 = tile + 2LL * gridDim.x;
+        if (next2 < full_tiles) load_tile(nxt2, next2);
+#elif AI_PREFETCH
         V nxt[kUnroll];
         const long long next = tile + gridDim.x;
         if (next < full_tiles) load_tile(nxt, next);
@@ -749,7 +757,10 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
             }
             st_stream(yv + base + (long long)u * kBlock, out);
         }
-#if AI_PREFETCH
+#if AI_PREFETCH == 2
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) { in[u] = nxt[u]; nxt[u] = nxt2[u]; }
+#elif AI_PREFETCH
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) in[u] = nxt[u];
 #endif
