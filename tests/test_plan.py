@@ -114,3 +114,55 @@ def test_rejects_malformed_tables(lib):
     assert lib.ai_table_plan(0, 3, 1, 1, None, None, 0, ctypes.byref(info)) == 1                         # AI_ERR_INVALID
     assert lib.ai_table_plan(0, 3, 1, 1, br.ctypes.data, co.ctypes.data, 0, None) == 1
     assert lib.ai_table_plan(9, 3, 1, 1, br.ctypes.data, co.ctypes.data, 0, ctypes.byref(info)) == 1
+
+
+def _random_breaks(rng, dtype, kind):
+    L = int(rng.integers(1, 400))
+    if kind == "dyadic":                     # what the reference's bisection produces
+        lo = float(rng.integers(-50, 50))
+        width = float(rng.choice([1.0, 3.0, 20.0, 0.375, 1e3]))
+        cuts = {0.0, 1.0}
+        for _ in range(L):
+            c = sorted(cuts)
+            k = int(rng.integers(0, len(c) - 1))
+            if c[k + 1] - c[k] > 2.0 ** -18:
+                cuts.add((c[k] + c[k + 1]) / 2)
+        b = lo + width * np.array(sorted(cuts))
+    elif kind == "uniform":
+        b = np.linspace(float(rng.integers(-5, 5)), float(rng.integers(6, 40)), L + 1)
+    else:
+        lo, hi = sorted(rng.uniform(-100, 100, 2))
+        b = np.concatenate([[lo], np.sort(rng.uniform(lo, hi, L - 1)), [hi]]) if L > 1 else np.array([lo, hi])
+    b = np.unique(b.astype(dtype))
+    return b if len(b) >= 2 else np.array([0, 1], dtype=dtype)
+
+
+@pytest.mark.parametrize("kind", ["dyadic", "uniform", "random"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_planner_invariants_on_random_tables(kind, dtype):
+    """Whatever the breakpoints, the plan fits the device and its flags are consistent."""
+    rng = np.random.default_rng(hash((kind, np.dtype(dtype).name)) % (2 ** 32))
+    seen = set()
+    for _ in range(60):
+        b = _random_breaks(rng, dtype, kind)
+        L = len(b) - 1
+        order = int(rng.integers(0, 14))
+        basis = ["chebyshev", "legendre", "monomial"][int(rng.integers(0, 3))]
+        f = tables.FlatTable(basis, order, dtype, b, rng.standard_normal((L, order + 1)).astype(dtype))
+        info = tables.plan(f)
+        seen.add((info["residency"], info["lookup_mode"], info["header_packed"], info["cell_records"]))
+        assert info["n_leaves"] == L and info["smem_bytes"] <= 227 * 1024
+        assert info["grid_cells"] >= 1 and info["search_steps"] >= 0
+        if info["lookup_mode"] == 2 or info["cell_records"] or info["header_packed"] == 2:
+            assert info["search_steps"] == 0                     # all need an exact grid
+        if info["header_packed"]:
+            assert basis != "monomial" and info["residency"] in (0, 1, 3)
+        if info["header_packed"] == 2:
+            assert info["cell_records"] or L <= 32 or dtype == np.float64
+        if info["residency"] == 4:
+            assert L == 2
+        if info["residency"] == 2:
+            assert info["smem_bytes"] == 0 and info["smem_resident"] == 0
+        if kind == "random" and L > 40:
+            assert info["header_packed"] == 0 and info["lookup_mode"] == 1     # arbitrary breakpoints: search
+    assert len(seen) >= 2
