@@ -12,6 +12,7 @@ ls -la gpurun_out/
 exit 0
 fi
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for sd in 1 2 3 4 5; do AI_TEST_SEED=$sd python -m pytest tests -m gpu -x -q -k lookup_exact_on_random_tables 2>&1 | tail -1; done
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err || exit 1
 python bench.py --order sorted --no-e2e --no-cpu --steps 50 > gpurun_out/bench_final_sorted.json 2>&1
 python bench.py --workload cfg3_j0_cheb_o13_f64 --steps 50 --no-e2e --no-cpu > gpurun_out/bench_final_cfg3.json 2>&1
