@@ -10,20 +10,14 @@ Reference data this reads (never writes):
 
 `flatten(approx)` works on any object carrying those attributes: the reference's own
 Approximator (all three pickle schema versions), this package's stand-in
-(approximator.py here), or a golden fixture record.
+(approximator.py here), or any record with the same attributes.
 """
 import ctypes
-import json
-import os
 import weakref
 
 import numpy as np
 
 from . import _cabi
-
-_GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                           "tests", "golden", "tables")
-
 
 class FlatTable(object):
     """Sorted breakpoints + per-leaf coefficients, in the table dtype."""
@@ -174,46 +168,6 @@ def flatten(approx):
             raise ValueError("Approximator tree_1d and interval_a/interval_b/coeff disagree")
     breaks = np.concatenate([a, b[-1:]])
     return FlatTable(approx.basis, n, dt, breaks, coef)
-
-
-class GoldenRecord(object):
-    """A frozen reference table + the reference's own evaluation of it (tests/golden/make_golden.py).
-    Carries the attributes of the reference Approximator that the hot path reads."""
-
-    def __init__(self, path):
-        d = np.load(path, allow_pickle=False)
-        self.meta = json.loads(str(d["meta"]))
-        m = self.meta
-        self.name = m["name"]
-        self.basis = m["basis"]
-        self.max_order = m["order"]
-        self.num_levels = m["num_levels"]
-        self.dtype = np.dtype(m["dtype"]).type
-        self.dtype_name = m["dtype_name"]
-        self.lower_bound = self.dtype(m["lower_bound"])
-        self.upper_bound = self.dtype(m["upper_bound"])
-        self.optimizations = list(m["optimizations"])
-        self.allowed_error = m["allowed_error"]
-        self.fmax = m["fmax"]
-        self.tree_1d = d["tree_1d"]
-        self.interval_a = list(d["interval_a"])
-        self.interval_b = list(d["interval_b"])
-        self.coeff = list(d["coeff"])
-        self.map = d["map"]
-        self.cmap = d["cmap"]
-        self.code, self.size, self.vector_width = 0, None, None
-        self.kernal = self.queue = self.tree_dev = self.x_dev = self.y_dev = None
-        self.x, self.y_ref, self.idx_ref, self.f_true = d["x"], d["y_ref"], d["idx_ref"], d["f_true"]
-
-
-def golden_names():
-    if not os.path.isdir(_GOLDEN_DIR):
-        return []
-    return sorted(f[:-4] for f in os.listdir(_GOLDEN_DIR) if f.endswith(".npz"))
-
-
-def load_golden(name):
-    return GoldenRecord(os.path.join(_GOLDEN_DIR, name + ".npz"))
 
 
 def plan(flat, smem_cap_bytes=0):

@@ -31,6 +31,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 import numpy as np  # noqa: E402
 
@@ -224,11 +225,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 
+    import golden_io                               # fixture loader (tests/golden/golden_io.py)
     from adaptive_interpolation_b200 import tables
     table_name, log2n, desc = WORKLOADS[args.workload]
     if args.log2_points is not None:
         log2n = args.log2_points
-    g = tables.load_golden(table_name)
+    g = golden_io.load_golden(table_name)
 
     if args.impl == "reference":
         run_reference_arm(args, args.workload, g, desc)

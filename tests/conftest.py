@@ -7,6 +7,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if GOLDEN not in sys.path:
+    sys.path.insert(0, GOLDEN)
+
+import golden_io  # noqa: E402  (tests/golden/golden_io.py: the fixture loader)
 
 REFERENCE_ROOT = "/root/reference"
 
@@ -21,8 +26,7 @@ def has_reference():
 
 @pytest.fixture(scope="session")
 def golden_names():
-    from adaptive_interpolation_b200 import tables
-    names = tables.golden_names()
+    names = golden_io.golden_names()
     assert len(names) >= 44, "golden fixtures missing: run tests/golden/make_golden.py"
     return names
 
@@ -31,15 +35,13 @@ _cache = {}
 
 
 def golden(name):
-    from adaptive_interpolation_b200 import tables
     if name not in _cache:
-        _cache[name] = tables.load_golden(name)
+        _cache[name] = golden_io.load_golden(name)
     return _cache[name]
 
 
 def all_golden_names():
-    from adaptive_interpolation_b200 import tables
-    return tables.golden_names()
+    return golden_io.golden_names()
 
 
 def value_tolerance(dtype, cond, ulps):

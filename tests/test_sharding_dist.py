@@ -13,6 +13,8 @@ from conftest import ROOT
 WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, %r)
+    sys.path.insert(0, os.path.join(%r, 'tests', 'golden'))
+    import golden_io
     import numpy as np
     import torch.distributed as dist
     from adaptive_interpolation_b200 import sharding, tables
@@ -20,7 +22,7 @@ WORKER = textwrap.dedent("""
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
                             rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
     rank, world = dist.get_rank(), dist.get_world_size()
-    g = tables.load_golden("approx__64o7-p1.19209289551e-06")
+    g = golden_io.load_golden("approx__64o7-p1.19209289551e-06")
     f = tables.flatten(g)
     n = 100003
     x = np.random.default_rng(7).uniform(0, 20, n)
@@ -35,7 +37,7 @@ WORKER = textwrap.dedent("""
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok", lo, hi)
-""") % ROOT
+""") % (ROOT, ROOT)
 
 
 @pytest.mark.timeout(180)

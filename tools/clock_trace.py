@@ -3,11 +3,13 @@
 import os, sys, threading, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import golden_io  # noqa: E402  (fixture loader, tests/golden/golden_io.py)
 import numpy as np, torch, pynvml
 from adaptive_interpolation_b200 import tables
 order = sys.argv[1] if len(sys.argv) > 1 else "random"
 pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
-g = tables.load_golden("approx__32o6-p1.19209289551e-06")
+g = golden_io.load_golden("approx__32o6-p1.19209289551e-06")
 tab = tables.DeviceTable(tables.flatten(g), 0)
 n = 1 << 28
 x = torch.clamp(torch.rand(n, device="cuda") * 20, max=19.999998)

@@ -4,12 +4,14 @@ memory directly over PCIe through UVA).  Prints Gpt/s and GB/s per direction."""
 import ctypes, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import golden_io  # noqa: E402  (fixture loader, tests/golden/golden_io.py)
 import numpy as np
 
 def one(n_log2=28):
     import torch
     from adaptive_interpolation_b200 import _cabi, tables
-    g = tables.load_golden("approx__32o6-p1.19209289551e-06")
+    g = golden_io.load_golden("approx__32o6-p1.19209289551e-06")
     tab = tables.DeviceTable(tables.flatten(g), 0)
     n = 1 << n_log2
     hp = ctypes.c_void_p()

@@ -13,6 +13,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import golden_io  # noqa: E402  (fixture loader, tests/golden/golden_io.py)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -44,7 +46,7 @@ def main():
         "group", "m", "points", "fused ms", "Gevals/s", "%hbm", "separ ms", "Gevals/s", "%hbm", "gain"))
     for gname, names in GROUPS.items():
         for m in range(2, len(names) + 1):
-            tabs = [tables.DeviceTable(tables.flatten(tables.load_golden(nm)), 0) for nm in names[:m]]
+            tabs = [tables.DeviceTable(tables.flatten(golden_io.load_golden(nm)), 0) for nm in names[:m]]
             dt = tabs[0].flat.dtype
             tdt = torch.float32 if dt == np.float32 else torch.float64
             esz = 4 if dt == np.float32 else 8

@@ -9,6 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import golden_io  # noqa: E402  (fixture loader, tests/golden/golden_io.py)
 TABLES = ["approx__32o6-p1.19209289551e-06", "approx__32o3-p1.19209289551e-06", "gen__cfg4_f1_leg_o7_f32",
           "gen__cfg4_f1_leg_o7_f64", "approximations__64o5-p2.22044604925e-14", "gen__j0_mono_o13_f64",
           "gen__cfg3_j0_cheb_o13_f64", "gen__line1_mono_o1_f64", "approx__64o13-p1.19209289551e-06",
@@ -20,7 +22,7 @@ def child():
     import torch
     from adaptive_interpolation_b200 import tables
     for name in TABLES:
-        g = tables.load_golden(name)
+        g = golden_io.load_golden(name)
         tab = tables.DeviceTable(tables.flatten(g), 0)
         info = tab.info()
         x = np.concatenate([g.x, np.sort(g.x[np.isfinite(g.x)])[:3000]])

@@ -13,6 +13,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import golden_io  # noqa: E402  (fixture loader, tests/golden/golden_io.py)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -70,7 +72,7 @@ def main():
           % (out["torch_copy_gbs"], out["ai_copy_gbs"], hbm, out["fma_peak_tflops_f32"], out["fma_peak_tflops_f64"]))
     del a, b
 
-    names = tables.golden_names() if args.tables == "all" else (BENCH_TABLES if args.tables == "bench" else args.tables.split(","))
+    names = golden_io.golden_names() if args.tables == "all" else (BENCH_TABLES if args.tables == "bench" else args.tables.split(","))
     print("%-42s %-9s %3s %-4s %5s %2s %7s | %9s %8s %6s | %9s %8s %6s" % (
         "table", "basis", "n", "T", "L", "K", "smemB", "rand ms", "Gpt/s", "%hbm", "sort ms", "Gpt/s", "%hbm"))
     for name in names:
@@ -86,7 +88,7 @@ def main():
             co = np.stack([C.chebfit(nodes, v, order) for v in vals]).astype(dt)
             f = tables.FlatTable("chebyshev", order, dt, br, co)
         else:
-            g = tables.load_golden(name)
+            g = golden_io.load_golden(name)
             f = tables.flatten(g)
         tab = tables.DeviceTable(f, 0)
         info = tab.info()
