@@ -18,6 +18,7 @@ BASIS_IDS = {"chebyshev": 0, "legendre": 1, "monomial": 2}
 DTYPE_F32, DTYPE_F64 = 0, 1
 MAX_ORDER = 16
 MAX_MULTI = 4
+TREE_LAYOUT_STANDARD, TREE_LAYOUT_TRIM = 0, 1
 
 # every symbol include/ai_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -27,7 +28,7 @@ EXPORTS = [
     "ai_eval_f32", "ai_eval_f64", "ai_eval_index_f32", "ai_eval_index_f64",
     "ai_eval_sum_f32", "ai_eval_sum_f64", "ai_eval_multi_f32", "ai_eval_multi_f64",
     "ai_eval_host_f32", "ai_eval_host_f64",
-    "ai_host_alloc", "ai_host_free", "ai_measure_fma_peak", "ai_copy_f32",
+    "ai_host_alloc", "ai_host_free", "ai_measure_fma_peak", "ai_copy_f32", "ai_measure_host_roundtrip",
 ]
 
 
@@ -92,6 +93,7 @@ def lib():
     L.ai_host_free.argtypes = [vp]
     L.ai_measure_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.ai_copy_f32.argtypes = [vp, vp, i64, i32, vp]
+    L.ai_measure_host_roundtrip.argtypes = [vp, vp, vp, i64]
     for name in EXPORTS:
         if name not in ("ai_last_error", "ai_version"):
             getattr(L, name).restype = ctypes.c_int

@@ -15,9 +15,20 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
+
+namespace ai {
+// one lock for every get-then-set of a kernel's dynamic shared memory limit (ai_inst.cuh, index_entry)
+std::mutex& smem_attr_mutex() {
+    static std::mutex mu;
+    return mu;
+}
+}  // namespace ai
 
 namespace {
 
@@ -61,6 +72,21 @@ int device_info(int device, DeviceInfo* out) {
     return AI_OK;
 }
 
+// No C++ exception may cross the extern "C" boundary (a huge n_leaves would otherwise end the
+// process with std::bad_alloc): every entry point that allocates runs inside guarded().
+template <typename F>
+int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(AI_ERR_UNSUPPORTED, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(AI_ERR_INVALID, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(AI_ERR_INVALID, "internal error");
+    }
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -97,8 +123,8 @@ struct HostPipe {
     void* dx[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
     void* dy[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    cudaEvent_t in_done[kHostSlots], k_done[kHostSlots], out_done[kHostSlots];
-    cudaEvent_t k_start[kHostSlots];
+    cudaEvent_t in_done[kHostSlots] = {}, k_done[kHostSlots] = {}, out_done[kHostSlots] = {};
+    cudaEvent_t k_start[kHostSlots] = {};
     std::mutex mu;
 };
 
@@ -122,6 +148,7 @@ struct ai_table {
     int packed = 0;                    // 1: records carry the one-element header (modes kSmemP / kSmemBankP)
     int cell_records = 0;              // 1: one record per coarse cell (view.rank_mode 2)
     int uniform_hdr = 0;               // 1: records carry no header, computed from the cell (modes kSmemU / kSmemBankU)
+    int rank16 = 0;                    // 1: the first[] section holds rank words (view.rank_mode bit 2)
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
@@ -143,6 +170,7 @@ struct GridPlan {
     unsigned cont = 0;
     int coarse_ok = 0;                   // div_* map a fine cell to its coarse cell, coarse_leaf is valid
     std::vector<uint32_t> coarse_leaf;   // leaf of every coarse cell
+    std::vector<uint32_t> rank16;        // Lookup::rank16_guess words (empty: not available)
 };
 
 long long gcd_ll(long long a, long long b) {
@@ -188,6 +216,30 @@ void plan_rank(const std::vector<double>& b, GridPlan* gp) {
     }
     gp->coarse_ok = 1; gp->div_mul = mul; gp->div_shift = sh; gp->div_add = add;
     gp->coarse_leaf.swap(coarse_leaf);
+    if (Gc > 32 && Gc <= 1024) {
+        // rank words: (continuation bits in all earlier words) << 16 | 16 continuation bits
+        std::vector<uint32_t> words((size_t)((Gc + 15) / 16), 0);
+        unsigned before = 0;
+        for (size_t w = 0; w < words.size(); ++w) {
+            unsigned bits = 0;
+            for (int j = 0; j < 16; ++j) {
+                const long long c = (long long)w * 16 + j;
+                if (c >= 1 && c < Gc && gp->coarse_leaf[(size_t)c] == gp->coarse_leaf[(size_t)(c - 1)]) bits |= (1u << j);
+            }
+            words[w] = (before << 16) | bits;
+            before += (unsigned)__builtin_popcount(bits);
+        }
+        bool ok = before < 65536u;
+        for (int g = 0; g < G && ok; ++g) {              // the device formula, for every fine cell
+            const unsigned gabs = (unsigned)(gp->g0 + g);
+            const unsigned c = (gabs * mul + add) >> sh;
+            const unsigned w = words[c >> 4];
+            const unsigned upto = (2u << (c & 15u)) - 1u;
+            const int leaf = (int)c - (int)(w >> 16) - __builtin_popcount(w & upto & 0xffffu);
+            ok = leaf == (int)gp->first[g];
+        }
+        if (ok) gp->rank16.swap(words);
+    }
     if (Gc > 32) return;
     unsigned cont = 0;
     for (long long c = 1; c < Gc; ++c)
@@ -418,12 +470,21 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     const int hdr = (t->basis == ai::kMono || uniform) ? 0 : (packed ? 1 : 2);
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
-    const int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
-    const int off_breaks = round_up16((size_t)gp.G * (size_t)(4 >> fshift));
+    int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
+    // the leaf as a rank from memory (Lookup::rank16_guess) where a first[] table would be read with
+    // bank conflicts: more than 128 bytes (32 words) of it, leaf-indexed records, no search
+    size_t rank16_min = 128;                             // (tuning hook: AI_B200_RANK16_MIN_BYTES)
+    if (const char* e = std::getenv("AI_B200_RANK16_MIN_BYTES")) rank16_min = (size_t)std::max(0L, std::atol(e));
+    const bool rank16 = !gp.rank16.empty() && !cell_records && gp.K == 0 && !gp.rank_mode
+                        && (size_t)gp.G * (size_t)(4 >> fshift) > rank16_min;
+    if (rank16) fshift = 3;
+    const int off_breaks = rank16 ? round_up16(gp.rank16.size() * 4) : round_up16((size_t)gp.G * (size_t)(4 >> fshift));
     const int off_records = off_breaks + round_up16((size_t)(L + 1 + pad) * sizeof(T));
     const size_t total = (size_t)off_records + (size_t)round_up16((size_t)NR * R * sizeof(T));
     image->assign(total, 0);
-    if (fshift == 2) {
+    if (rank16) {
+        std::memcpy(image->data() + off_first, gp.rank16.data(), gp.rank16.size() * sizeof(uint32_t));
+    } else if (fshift == 2) {
         for (int g = 0; g < gp.G; ++g) (*image)[off_first + g] = (unsigned char)gp.first[g];
     } else if (fshift == 1) {
         uint16_t* f16 = reinterpret_cast<uint16_t*>(image->data() + off_first);
@@ -460,6 +521,7 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     t->view.n_records_elems = (int)(NR * R);
     t->view.n_records = (int)NR;
     t->cell_records = cell_records ? 1 : 0;
+    t->rank16 = rank16 ? 1 : 0;
     t->view.n_breaks_elems = (int)(L + 1 + pad);
     t->view.off_first = off_first;
     t->view.off_breaks = off_breaks;
@@ -523,7 +585,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
                                                          : plan_uniform_header<double>(t, gp);
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
     const int full_copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
-    int mode = ai::kSmem, copies = 1;
+    int mode = ai::kSmem, copies = 1, bcopies = 1;
     bool go_global = false;
     // First with one record per coarse cell (when the grid allows it); kept only if the gathers
     // stay conflict-free -- packed with one record per bank, or fully replicated.  Otherwise
@@ -557,14 +619,27 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         if (soff_r) *soff_r = (int)orr;
         return orr + (size_t)round_up16((size_t)t->view.n_records_elems * esz * cp);
     };
+    // kSmemV: [grid / rank words][breaks x bcp][16-byte padded leaf records x 8], 128-bit gathers
+    auto vec_layout = [&](int bcp) -> size_t {
+        const size_t Rg = (size_t)ai::rec_stride_global(t->basis, t->order, (int)esz);
+        return (size_t)t->view.off_breaks + (size_t)round_up16((size_t)t->view.n_breaks_elems * esz * bcp)
+               + (size_t)round_up16((size_t)L * Rg * esz * ai::kVecCopies);
+    };
     // leaves a warp can address without two of them sharing a bank (odd record stride)
     const int64_t conflict_free_leaves = full_copies;
-    mode = ai::kSmem; copies = 1;
+    mode = ai::kSmem; copies = 1; bcopies = 1;
     if (go_global) {
         mode = ai::kGlobal;
-    } else if (NR > conflict_free_leaves || forced == ai::kSmemBank || forced == ai::kSmemBankN) {
-        if (bank_layout(full_copies, nullptr, nullptr) <= smem_cap && forced != ai::kSmemBankN) {
+    } else if (NR > conflict_free_leaves || forced == ai::kSmemBank || forced == ai::kSmemBankN || forced == ai::kSmemV) {
+        const bool vec_ok = !t->cell_records && !std::getenv("AI_B200_NO_VEC_MODE") && forced != ai::kSmemBankN
+                            && (forced == ai::kSmemV || forced < 0);
+        if (bank_layout(full_copies, nullptr, nullptr) <= smem_cap && forced != ai::kSmemBankN && forced != ai::kSmemV) {
             mode = ai::kSmemBank; copies = full_copies;
+        } else if (vec_ok && vec_layout(1) <= smem_cap) {
+            // full per-bank replication does not fit: 8 copies of 16-byte padded records, 128-bit loads
+            // (conflict-free per quarter-warp); the breakpoints per bank too when a search reads them
+            mode = ai::kSmemV; copies = ai::kVecCopies;
+            bcopies = (gp.K > 0 && vec_layout(full_copies) <= smem_cap) ? full_copies : 1;
         } else if (gp.K == 0 || forced == ai::kSmemBankN) {
             // partial replication pays only when no search follows (measured: the 429-leaf 64o5
             // table 39% -> 44% of HBM on random points; config 4's 220-leaf K=6 table gets slower)
@@ -577,6 +652,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     const bool layout_ok = !t->cell_records || NR == L ||
                            (mode == ai::kGlobal && (!leaf_image_fits || forced == ai::kGlobal)) ||
                            mode == ai::kSmemBank || (mode == ai::kSmem && NR <= conflict_free_leaves);
+    if (mode == ai::kSmemBank || mode == ai::kSmemBankN) bcopies = copies;
     // only these have computed-header kernels (the bank form for fp64 only)
     const bool header_ok = !t->uniform_hdr || mode == ai::kSmem || (mode == ai::kSmemBank && t->dtype == AI_DTYPE_F64);
     if (layout_ok && header_ok) break;
@@ -588,6 +664,13 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         if (soff_r) *soff_r = (int)orr;
         return orr + (size_t)round_up16((size_t)t->view.n_records_elems * esz * cp);
     };
+    if (mode == ai::kSmemV) {
+        // the records in the 16-byte padded global layout ([a, 2/(b-a), c0..cn, pad]), one per leaf
+        rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image, nullptr, false)
+                                        : build_image<double>(t, gp, true, &image, nullptr, false);
+        if (rc) return rc;
+        if (t->cell_records) return fail(AI_ERR_TABLE, "internal: kSmemV planned with cell-indexed records");
+    }
     // two leaves: both records ride in the kernel parameters, element-wise select instead of a gather
     // (the image stays: the reduction and multi-table kernels read it)
     if (!go_global && ((L == 2 && forced < 0) || (L <= 2 && forced == ai::kSelect))) {
@@ -617,17 +700,23 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->mode = mode;
     t->copies = copies;
     t->view.copies = copies;
+    t->view.bcopies = bcopies;
     t->smem_resident = (mode != ai::kGlobal);
     t->eval_smem = 0;
     if (mode == ai::kSmem || mode == ai::kSmemP || mode == ai::kSmemU) t->eval_smem = t->view.image_bytes;
-    if (ai::mode_bank(mode))
+    if (mode == ai::kSmemV) {
+        t->view.soff_breaks = t->view.off_breaks;
+        t->view.soff_records = t->view.off_breaks + round_up16((size_t)t->view.n_breaks_elems * esz * bcopies);
+        t->eval_smem = t->view.soff_records + round_up16((size_t)t->view.n_records_elems * esz * ai::kVecCopies);
+    } else if (ai::mode_bank(mode)) {
         t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
+    }
     t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
     t->view.image = nullptr;
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
-    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0);
+    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0) | (t->rank16 ? 4 : 0);
     t->view.div_mul = gp.div_mul;
     t->view.div_shift = gp.div_shift;
     t->view.div_add = gp.div_add;
@@ -664,13 +753,23 @@ int finish_table(ai_table* t) {
     rc = prepare_dispatch(t->basis, t->dtype, t->order, t->mode, t->eval_smem, &bps);
     if (rc) return rc;
     if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->eval_smem);
-    if (t->mode != ai::kGlobal && t->aux_smem > 48 * 1024) {
+    if (t->mode != ai::kGlobal && t->mode != ai::kSmemV && t->aux_smem > 48 * 1024) {
         int dummy = 0;      // opt the reduction kernel (packed layout) into large shared memory too
         rc = prepare_dispatch(t->basis, t->dtype, t->order,
                               t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem), t->aux_smem, &dummy);
         if (rc) return rc;
     }
     t->blocks_per_sm = bps;
+    return AI_OK;
+}
+
+// before anything is allocated for the table
+int check_leaf_count(int64_t n_leaves, int order) {
+    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
+    if (n_leaves > kMaxLeaves)
+        return fail(AI_ERR_UNSUPPORTED, "more than %lld leaves (%lld) not supported", (long long)kMaxLeaves, (long long)n_leaves);
+    if (n_leaves * (int64_t)(order + 4) * 8 > (int64_t)1 << 30)
+        return fail(AI_ERR_UNSUPPORTED, "table image would exceed 1 GiB (%lld leaves, order %d)", (long long)n_leaves, order);
     return AI_OK;
 }
 
@@ -771,7 +870,12 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     int rc = device_info(t0->device, &prop);
     if (rc) return rc;
     const uintptr_t ax = reinterpret_cast<uintptr_t>(x);
-    bool fuse = (m >= 2) && !std::getenv("AI_B200_NO_FUSED_MULTI") && (ax % sizeof(T)) == 0;
+    // Fusing saves (m - 1) reads of x but keeps every table's record gathers; it pays while a record is
+    // short (measured, profiles/r1_multi_table.txt: fp32 / fp64 order 6 gain 1.07-1.41x, fp64 order 13
+    // on random points 0.95x), so long records take the per-table launches.  Test hook:
+    // AI_B200_FORCE_FUSED_MULTI=1 fuses whenever the shapes allow it.
+    const bool short_records = (size_t)(t0->order + 1) * sizeof(T) <= 64 || std::getenv("AI_B200_FORCE_FUSED_MULTI");
+    bool fuse = (m >= 2) && short_records && !std::getenv("AI_B200_NO_FUSED_MULTI") && (ax % sizeof(T)) == 0;
     size_t smem = 0;
     ai::MultiArgs args{};
     for (int j = 0; j < m && fuse; ++j) {
@@ -836,6 +940,7 @@ int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* st
         ai::index_kernel<T, ai::kGlobal><<<grid, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
     } else {
         if (t->aux_smem > 48 * 1024) {
+            std::lock_guard<std::mutex> lock(ai::smem_attr_mutex());
             cudaFuncAttributes fa;
             AI_CUDA(cudaFuncGetAttributes(&fa, ai::index_kernel<T, ai::kSmem>));
             if (fa.maxDynamicSharedSizeBytes < t->aux_smem)
@@ -865,8 +970,11 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     cfg.stream = s;
     cfg.select = nullptr;
     cudaError_t e;
-    const int m = (t->mode == ai::kGlobal) ? ai::kGlobal
-                                           : (t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem));
+    // (a kSmemV table's image holds global-layout records: its reduction runs the L2-resident kernel)
+    const bool from_global = t->mode == ai::kGlobal || t->mode == ai::kSmemV;
+    if (from_global) cfg.smem_bytes = 0;
+    const int m = from_global ? ai::kGlobal
+                              : (t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem));
     if constexpr (sizeof(T) == 4) {
         if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, m, cfg, t->view, x, result, n);
         else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, m, cfg, t->view, x, result, n);
@@ -881,9 +989,19 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
 }
 
 // ------------------------------------------------------------------ host-buffer pipeline
+void pipe_destroy(ai_table* t);
+
+int pipe_init_body(ai_table* t, size_t elem);
+
 int pipe_init(ai_table* t, size_t elem) {
+    if (t->pipe.ready) return AI_OK;
+    const int rc = pipe_init_body(t, elem);
+    if (rc) pipe_destroy(t);           // a partial pipeline (some buffers / events) is released, not leaked
+    return rc;
+}
+
+int pipe_init_body(ai_table* t, size_t elem) {
     HostPipe& p = t->pipe;
-    if (p.ready) return AI_OK;
     long mib = 32;                                            // MiB per direction per slot
     if (const char* e = std::getenv("AI_B200_HOST_CHUNK_MB")) { const long v = std::atol(e); if (v >= 1 && v <= 1024) mib = v; }
     if (const char* e = std::getenv("AI_B200_HOST_SLOTS")) { const long v = std::atol(e); if (v >= 2 && v <= kHostSlots) p.slots = (int)v; }
@@ -905,18 +1023,67 @@ int pipe_init(ai_table* t, size_t elem) {
 
 void pipe_destroy(ai_table* t) {
     HostPipe& p = t->pipe;
-    if (!p.ready) return;
-    for (int s = 0; s < p.slots; ++s) {
-        cudaFree(p.dx[s]); cudaFree(p.dy[s]);
-        cudaEventDestroy(p.in_done[s]); cudaEventDestroy(p.out_done[s]);
-        cudaEventDestroy(p.k_start[s]); cudaEventDestroy(p.k_done[s]);
+    for (int s = 0; s < kHostSlots; ++s) {
+        if (p.dx[s]) cudaFree(p.dx[s]);
+        if (p.dy[s]) cudaFree(p.dy[s]);
+        if (p.in_done[s]) cudaEventDestroy(p.in_done[s]);
+        if (p.out_done[s]) cudaEventDestroy(p.out_done[s]);
+        if (p.k_start[s]) cudaEventDestroy(p.k_start[s]);
+        if (p.k_done[s]) cudaEventDestroy(p.k_done[s]);
+        p.dx[s] = p.dy[s] = nullptr;
+        p.in_done[s] = p.out_done[s] = p.k_start[s] = p.k_done[s] = nullptr;
     }
-    cudaStreamDestroy(p.s_in); cudaStreamDestroy(p.s_k); cudaStreamDestroy(p.s_out);
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_k) cudaStreamDestroy(p.s_k);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    p.s_in = p.s_k = p.s_out = nullptr;
     p.ready = false;
 }
 
+// One pass of the 3-stage pipeline over n host elements: chunk c is copied in on s_in, evaluated on
+// s_k and copied out on s_out, `slots` chunks in flight.  with_kernel = false moves the same bytes
+// with no kernel between the copies: the plain-copy ceiling of this host / link, measured through
+// the very same code path (ai_measure_host_roundtrip).
 template <typename T>
-int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_ms) {
+int host_pipeline_pass(ai_table* t, const T* x, T* y, int64_t n, bool with_kernel, double* ms_total) {
+    HostPipe& p = t->pipe;
+    const int64_t nchunks = (n + p.chunk - 1) / p.chunk;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % p.slots);
+        const int64_t off = c * p.chunk, m = std::min<int64_t>(p.chunk, n - off);
+        if (c >= p.slots) {
+            // slot reuse: its previous D2H must have drained before we overwrite dx/dy
+            AI_CUDA(cudaEventSynchronize(p.out_done[s]));
+            float ms = 0.f;
+            AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
+            *ms_total += ms;
+        }
+        AI_CUDA(cudaMemcpyAsync(p.dx[s], x + off, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, p.s_in));
+        AI_CUDA(cudaEventRecord(p.in_done[s], p.s_in));
+        AI_CUDA(cudaStreamWaitEvent(p.s_k, p.in_done[s], 0));
+        AI_CUDA(cudaEventRecord(p.k_start[s], p.s_k));
+        if (with_kernel) {
+            const int rc = launch_eval_t<T>(t, static_cast<const T*>(p.dx[s]), static_cast<T*>(p.dy[s]), m, p.s_k);
+            if (rc) return rc;
+        }
+        AI_CUDA(cudaEventRecord(p.k_done[s], p.s_k));
+        AI_CUDA(cudaStreamWaitEvent(p.s_out, p.k_done[s], 0));
+        AI_CUDA(cudaMemcpyAsync(y + off, p.dy[s], (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, p.s_out));
+        AI_CUDA(cudaEventRecord(p.out_done[s], p.s_out));
+    }
+    AI_CUDA(cudaStreamSynchronize(p.s_out));
+    const int64_t first_pending = std::max<int64_t>(0, nchunks - p.slots);
+    for (int64_t c = first_pending; c < nchunks; ++c) {
+        const int s = (int)(c % p.slots);
+        float ms = 0.f;
+        AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
+        *ms_total += ms;
+    }
+    return AI_OK;
+}
+
+template <typename T>
+int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_ms, bool with_kernel = true) {
     if (kernel_ms) *kernel_ms = 0.0;
     if (!ct) return fail(AI_ERR_INVALID, "table handle is NULL");
     if (n < 0) return fail(AI_ERR_INVALID, "n = %lld is negative", (long long)n);
@@ -929,37 +1096,15 @@ int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_m
     std::lock_guard<std::mutex> lock(t->pipe.mu);
     int rc = pipe_init(t, sizeof(T));
     if (rc) return rc;
-    HostPipe& p = t->pipe;
-    const int64_t nchunks = (n + p.chunk - 1) / p.chunk;
     double ms_total = 0.0;
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int s = (int)(c % p.slots);
-        const int64_t off = c * p.chunk, m = std::min<int64_t>(p.chunk, n - off);
-        if (c >= p.slots) {
-            // slot reuse: its previous D2H must have drained before we overwrite dx/dy
-            AI_CUDA(cudaEventSynchronize(p.out_done[s]));
-            float ms = 0.f;
-            AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
-            ms_total += ms;
-        }
-        AI_CUDA(cudaMemcpyAsync(p.dx[s], x + off, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, p.s_in));
-        AI_CUDA(cudaEventRecord(p.in_done[s], p.s_in));
-        AI_CUDA(cudaStreamWaitEvent(p.s_k, p.in_done[s], 0));
-        AI_CUDA(cudaEventRecord(p.k_start[s], p.s_k));
-        rc = launch_eval_t<T>(t, static_cast<const T*>(p.dx[s]), static_cast<T*>(p.dy[s]), m, p.s_k);
-        if (rc) return rc;
-        AI_CUDA(cudaEventRecord(p.k_done[s], p.s_k));
-        AI_CUDA(cudaStreamWaitEvent(p.s_out, p.k_done[s], 0));
-        AI_CUDA(cudaMemcpyAsync(y + off, p.dy[s], (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, p.s_out));
-        AI_CUDA(cudaEventRecord(p.out_done[s], p.s_out));
-    }
-    AI_CUDA(cudaStreamSynchronize(p.s_out));
-    const int64_t first_pending = std::max<int64_t>(0, nchunks - p.slots);
-    for (int64_t c = first_pending; c < nchunks; ++c) {
-        const int s = (int)(c % p.slots);
-        float ms = 0.f;
-        AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
-        ms_total += ms;
+    rc = host_pipeline_pass<T>(t, x, y, n, with_kernel, &ms_total);
+    if (rc) {
+        // no copy into (or out of) the caller's buffers may still be in flight when we return
+        const std::string msg = g_err;
+        HostPipe& p = t->pipe;
+        cudaStreamSynchronize(p.s_in); cudaStreamSynchronize(p.s_k); cudaStreamSynchronize(p.s_out);
+        g_err = msg;
+        return rc;
     }
     if (kernel_ms) *kernel_ms = ms_total;
     return AI_OK;
@@ -1047,13 +1192,16 @@ int ai_table_create(int basis, int order, int dtype, int64_t n_leaves, const voi
     *out = nullptr;
     int rc = check_common(basis, order, dtype, device);
     if (rc) return rc;
-    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
+    rc = check_leaf_count(n_leaves, order);
+    if (rc) return rc;
     if (!breaks || !coef) return fail(AI_ERR_INVALID, "breaks or coef is NULL");
-    ai_table* t = table_from_flat(basis, order, dtype, n_leaves, breaks, coef, device);
-    rc = finish_table(t);
-    if (rc) { ai_table_destroy(t); return rc; }
-    *out = t;
-    return AI_OK;
+    return guarded([&]() -> int {
+        ai_table* t = table_from_flat(basis, order, dtype, n_leaves, breaks, coef, device);
+        const int rc2 = finish_table(t);
+        if (rc2) { ai_table_destroy(t); return rc2; }
+        *out = t;
+        return AI_OK;
+    });
 }
 
 int ai_table_plan(int basis, int order, int dtype, int64_t n_leaves, const void* breaks, const void* coef,
@@ -1061,18 +1209,20 @@ int ai_table_plan(int basis, int order, int dtype, int64_t n_leaves, const void*
     if (!info) return fail(AI_ERR_INVALID, "info is NULL");
     int rc = check_shape(basis, order, dtype);
     if (rc) return rc;
-    if (n_leaves < 1) return fail(AI_ERR_TABLE, "a table needs at least one leaf (got %lld)", (long long)n_leaves);
+    rc = check_leaf_count(n_leaves, order);
+    if (rc) return rc;
     if (!breaks || !coef) return fail(AI_ERR_INVALID, "breaks or coef is NULL");
     if (smem_cap_bytes <= 0) smem_cap_bytes = 227 * 1024;        // sm_100: opt-in shared memory per CTA
-    ai_table* t = table_from_flat(basis, order, dtype, n_leaves, breaks, coef, -1);
-    std::vector<unsigned char> image;
-    rc = plan_table(t, (size_t)smem_cap_bytes, &image);
-    if (rc == AI_OK) {
-        t->blocks_per_sm = 0; t->sm_count = 0;
-        rc = ai_table_get_info(t, info);
-    }
-    delete t;
-    return rc;
+    return guarded([&]() -> int {
+        std::unique_ptr<ai_table> t(table_from_flat(basis, order, dtype, n_leaves, breaks, coef, -1));
+        std::vector<unsigned char> image;
+        int rc2 = plan_table(t.get(), (size_t)smem_cap_bytes, &image);
+        if (rc2 == AI_OK) {
+            t->blocks_per_sm = 0; t->sm_count = 0;
+            rc2 = ai_table_get_info(t.get(), info);
+        }
+        return rc2;
+    });
 }
 
 int ai_table_create_from_tree(int basis, int order, int dtype, int num_levels, int layout,
@@ -1085,67 +1235,96 @@ int ai_table_create_from_tree(int basis, int order, int dtype, int num_levels, i
     if (layout != AI_TREE_LAYOUT_STANDARD && layout != AI_TREE_LAYOUT_TRIM)
         return fail(AI_ERR_INVALID, "unknown tree layout %d", layout);
     if (num_levels < 1) return fail(AI_ERR_INVALID, "num_levels %d < 1", num_levels);
-    auto at = [&](int64_t k) -> double {
-        return dtype == AI_DTYPE_F32 ? (double)static_cast<const float*>(tree_1d)[k]
-                                     : static_cast<const double*>(tree_1d)[k];
-    };
-    const int n = order;
-    std::vector<double> a, b, coef;
-    // Iterative in-order traversal over element offsets, following the child links the way
-    // Approximator.evaluate does (approximator.py:274-290).  Standard layout: children are
-    // ELEMENT offsets at [n+4], [n+5], leaves point to themselves (approximator.py:198-199).
-    // trim_data layout: children are NODE indices at [1], [2]; node k starts at the k-th
-    // record boundary, so build the offset table first (inner nodes have 3 elements,
-    // leaves n+6).
-    if (layout == AI_TREE_LAYOUT_TRIM)
-        return fail(AI_ERR_UNSUPPORTED, "trim_data tree layout: the reference's own evaluator indexes it "
-                    "inconsistently (approximator.py:202-206 vs :275-290); flatten on the host instead");
-    const int stride = n + 6;
-    if (n_elems % stride) return fail(AI_ERR_TABLE, "tree_1d length %lld is not a multiple of the node stride %d",
-                                      (long long)n_elems, stride);
-    const int64_t n_nodes = n_elems / stride;
-    struct Frame { int64_t off; int state; };
-    std::vector<Frame> stack;
-    stack.push_back({0, 0});
-    int64_t visited = 0;
-    while (!stack.empty()) {
-        Frame& fr = stack.back();
-        const int64_t o = fr.off;
-        if (o < 0 || o + stride > n_elems || (o % stride)) return fail(AI_ERR_TABLE, "child offset %lld out of range", (long long)o);
-        const int64_t lo = (int64_t)at(o + n + 4), ro = (int64_t)at(o + n + 5);
-        const bool leaf = (lo == o) || (ro == o);
-        if (leaf) {
-            a.push_back(at(o + n + 2));
-            b.push_back(at(o + n + 3));
-            for (int j = 0; j <= n; ++j) coef.push_back(at(o + 1 + j));
-            stack.pop_back();
-        } else if (fr.state == 0) {
-            fr.state = 1;
-            stack.push_back({lo, 0});
-        } else if (fr.state == 1) {
-            fr.state = 2;
-            stack.push_back({ro, 0});
+    if (n_elems / 3 > 2 * kMaxLeaves) return fail(AI_ERR_UNSUPPORTED, "tree_1d of %lld elements is too large", (long long)n_elems);
+    return guarded([&]() -> int {
+        auto at = [&](int64_t k) -> double {
+            return dtype == AI_DTYPE_F32 ? (double)static_cast<const float*>(tree_1d)[k]
+                                         : static_cast<const double*>(tree_1d)[k];
+        };
+        const int n = order;
+        const int stride = n + 6;
+        std::vector<double> a, b, coef;
+        if (layout == AI_TREE_LAYOUT_TRIM) {
+            // "trim_data" (approximator.py:202-206, 232-233): nodes in preorder, a leaf is
+            // [mid, self, self, c0..cn, a, b] (both links equal), an inner node is
+            // [mid, left NODE index, right NODE index] (never equal).  The reference's own tree_1d walk
+            // reads those node indices as element offsets (approximator.py:275-290), so the links
+            // cannot be followed; but preorder visits the leaves left to right, which is all the
+            // flattening needs.  The links are still checked: left child = next node, right child
+            // = the node after the left subtree.
+            std::vector<int64_t> pending_right;          // right-child node indices still expected
+            int64_t node = 0, o = 0;
+            while (o < n_elems) {
+                if (o + 3 > n_elems) return fail(AI_ERR_TABLE, "trim_data tree_1d ends inside node %lld", (long long)node);
+                if (!pending_right.empty() && pending_right.back() == node) pending_right.pop_back();
+                const double l = at(o + 1), r = at(o + 2);
+                if (l == r) {                            // leaf
+                    if (o + stride > n_elems) return fail(AI_ERR_TABLE, "trim_data tree_1d ends inside leaf node %lld", (long long)node);
+                    for (int j = 0; j <= n; ++j) coef.push_back(at(o + 3 + j));
+                    a.push_back(at(o + n + 4));
+                    b.push_back(at(o + n + 5));
+                    o += stride;
+                } else {
+                    if ((int64_t)l != node + 1) return fail(AI_ERR_TABLE, "trim_data node %lld: left child %g is not the next node", (long long)node, l);
+                    pending_right.push_back((int64_t)r);
+                    o += 3;
+                }
+                ++node;
+            }
+            if (!pending_right.empty()) return fail(AI_ERR_TABLE, "trim_data tree_1d: right child %lld never reached", (long long)pending_right.back());
+            if ((int64_t)a.size() * 2 - 1 != node) return fail(AI_ERR_TABLE, "trim_data tree_1d is not a full binary tree (%lld nodes, %lld leaves)", (long long)node, (long long)a.size());
         } else {
-            stack.pop_back();
+            // Iterative traversal over element offsets, following the child links the way
+            // Approximator.evaluate does (approximator.py:274-290): children are ELEMENT offsets at
+            // [n+4], [n+5], leaves point to themselves (approximator.py:198-199).
+            if (n_elems % stride) return fail(AI_ERR_TABLE, "tree_1d length %lld is not a multiple of the node stride %d",
+                                              (long long)n_elems, stride);
+            const int64_t n_nodes = n_elems / stride;
+            struct Frame { int64_t off; int state; };
+            std::vector<Frame> stack;
+            stack.push_back({0, 0});
+            int64_t visited = 0;
+            while (!stack.empty()) {
+                Frame& fr = stack.back();
+                const int64_t o = fr.off;
+                if (o < 0 || o + stride > n_elems || (o % stride)) return fail(AI_ERR_TABLE, "child offset %lld out of range", (long long)o);
+                const int64_t lo = (int64_t)at(o + n + 4), ro = (int64_t)at(o + n + 5);
+                const bool leaf = (lo == o) || (ro == o);
+                if (leaf) {
+                    a.push_back(at(o + n + 2));
+                    b.push_back(at(o + n + 3));
+                    for (int j = 0; j <= n; ++j) coef.push_back(at(o + 1 + j));
+                    stack.pop_back();
+                } else if (fr.state == 0) {
+                    fr.state = 1;
+                    stack.push_back({lo, 0});
+                } else if (fr.state == 1) {
+                    fr.state = 2;
+                    stack.push_back({ro, 0});
+                } else {
+                    stack.pop_back();
+                }
+                if (++visited > 4 * n_nodes + 8) return fail(AI_ERR_TABLE, "tree_1d child links form a cycle");
+                if ((int64_t)stack.size() > n_nodes + 1) return fail(AI_ERR_TABLE, "tree_1d deeper than its node count");
+            }
         }
-        if (++visited > 4 * n_nodes + 8) return fail(AI_ERR_TABLE, "tree_1d child links form a cycle");
-        if ((int64_t)stack.size() > n_nodes + 1) return fail(AI_ERR_TABLE, "tree_1d deeper than its node count");
-    }
-    const int64_t L = (int64_t)a.size();
-    if (L < 1) return fail(AI_ERR_TABLE, "tree has no leaves");
-    for (int64_t k = 0; k + 1 < L; ++k)
-        if (b[k] != a[k + 1]) return fail(AI_ERR_TABLE, "leaves %lld and %lld are not contiguous (%.17g != %.17g)",
-                                          (long long)k, (long long)k + 1, b[k], a[k + 1]);
-    (void)num_levels;
-    ai_table* t = new ai_table;
-    t->basis = basis; t->order = order; t->dtype = dtype; t->device = device; t->L = L;
-    t->breaks = a;
-    t->breaks.push_back(b.back());
-    t->coef = coef;
-    rc = finish_table(t);
-    if (rc) { ai_table_destroy(t); return rc; }
-    *out = t;
-    return AI_OK;
+        const int64_t L = (int64_t)a.size();
+        if (L < 1) return fail(AI_ERR_TABLE, "tree has no leaves");
+        for (int64_t k = 0; k + 1 < L; ++k)
+            if (b[k] != a[k + 1]) return fail(AI_ERR_TABLE, "leaves %lld and %lld are not contiguous (%.17g != %.17g)",
+                                              (long long)k, (long long)k + 1, b[k], a[k + 1]);
+        int rc2 = check_leaf_count(L, order);
+        if (rc2) return rc2;
+        ai_table* t = new ai_table;
+        t->basis = basis; t->order = order; t->dtype = dtype; t->device = device; t->L = L;
+        t->breaks = a;
+        t->breaks.push_back(b.back());
+        t->coef = coef;
+        rc2 = finish_table(t);
+        if (rc2) { ai_table_destroy(t); return rc2; }
+        *out = t;
+        return AI_OK;
+    });
 }
 
 int ai_table_destroy(ai_table_t* t) {
@@ -1171,7 +1350,7 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->cell_records = t->cell_records;
     info->bank_copies = t->copies;
     info->smem_resident = t->smem_resident;
-    info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : 0);
+    info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : (t->rank16 ? 3 : 0));
     info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;
     info->lower_bound = t->breaks.front(); info->upper_bound = t->breaks.back();
     return AI_OK;
@@ -1203,6 +1382,12 @@ int ai_eval_multi_f64(const ai_table_t* const* t, int m, const double* x, double
 }
 int ai_eval_host_f32(const ai_table_t* t, const float* x, float* y, int64_t n, double* ms) { return host_entry<float>(t, x, y, n, ms); }
 int ai_eval_host_f64(const ai_table_t* t, const double* x, double* y, int64_t n, double* ms) { return host_entry<double>(t, x, y, n, ms); }
+
+int ai_measure_host_roundtrip(const ai_table_t* t, const void* x, void* y, int64_t n) {
+    if (!t) return fail(AI_ERR_INVALID, "table handle is NULL");
+    if (t->dtype == AI_DTYPE_F32) return host_entry<float>(t, static_cast<const float*>(x), static_cast<float*>(y), n, nullptr, false);
+    return host_entry<double>(t, static_cast<const double*>(x), static_cast<double*>(y), n, nullptr, false);
+}
 
 int ai_host_alloc(void** p, int64_t bytes) {
     if (!p || bytes < 0) return fail(AI_ERR_INVALID, "bad arguments");

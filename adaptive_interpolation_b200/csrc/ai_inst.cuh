@@ -5,7 +5,10 @@
 #pragma once
 #include "ai_kernels.cuh"
 
+#include <mutex>
+
 namespace ai {
+std::mutex& smem_attr_mutex();          // ai_api.cu: serialises the get-then-set below across threads
 namespace {
 
 constexpr int kMaxOrder = 16;
@@ -16,6 +19,7 @@ constexpr int kMaxOrder = 16;
 template <typename K>
 cudaError_t raise_smem_limit(K kernel, int smem_bytes) {
     if (smem_bytes <= 48 * 1024) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(smem_attr_mutex());
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
     if (e != cudaSuccess) return e;
@@ -77,6 +81,7 @@ struct Switch {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::eval(a...);
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::eval(a...);
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::eval(a...);
+            if (mode == kSmemV) return Unit<BASIS, T, ORDER, kSmemV>::eval(a...);
             if constexpr (BASIS != kMono) {          // the monomial record has no header to pack
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::eval(a...);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::eval(a...);
@@ -120,6 +125,7 @@ struct Switch {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::prepare(smem_bytes, bps);
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::prepare(smem_bytes, bps);
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::prepare(smem_bytes, bps);
+            if (mode == kSmemV) return Unit<BASIS, T, ORDER, kSmemV>::prepare(smem_bytes, bps);
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::prepare(smem_bytes, bps);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::prepare(smem_bytes, bps);

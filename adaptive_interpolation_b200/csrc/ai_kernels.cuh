@@ -87,12 +87,20 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              2/(b-a); the kernel computes both from the cell index (I2F + FMA) instead of
 //              gathering them: two more wavefronts off the return path.  Verified per cell on the
 //              host against the stored header, bit for bit.
+//   kSmemV     tables whose full per-bank replication does not fit in shared memory (hundreds of fp64
+//              leaves): records in the 16-byte padded global layout, EIGHT copies, fetched with
+//              128-bit loads.  A 128-bit shared load is served a quarter-warp (8 lanes) at a time, so
+//              8 copies -- lane l reads copy l mod 8, each copy in its own 16-byte bank group -- make
+//              the gather conflict-free with a quarter (fp32) / half (fp64) of the memory the
+//              per-bank layouts need.  Breakpoints (read by the search, if any) are replicated
+//              per bank when they fit beside the records.
 enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4, kSmemP = 5, kSmemBankP = 6,
-             kSmemU = 7, kSmemBankU = 8 };
+             kSmemU = 7, kSmemBankU = 8, kSmemV = 9 };
+constexpr int kVecCopies = 8;
 __host__ __device__ constexpr bool mode_packed_hdr(int mode) { return mode == kSmemP || mode == kSmemBankP; }
 __host__ __device__ constexpr bool mode_uniform_hdr(int mode) { return mode == kSmemU || mode == kSmemBankU; }
 __host__ __device__ constexpr bool mode_bank(int mode) {
-    return mode == kSmemBank || mode == kSmemBankN || mode == kSmemBankP || mode == kSmemBankU;
+    return mode == kSmemBank || mode == kSmemBankN || mode == kSmemBankP || mode == kSmemBankU || mode == kSmemV;
 }
 constexpr int kMaxRecord = 16 + 1 + 2;         // AI_MAX_ORDER + 1 coefficients + [a, 2/(b-a)]
 // kSelect's table, passed by value as a kernel parameter; empty in every other mode
@@ -116,13 +124,17 @@ struct TableView {
     int n_leaves;                  // L
     int n_records_elems;           // L * R (elements in the packed record array)
     int n_breaks_elems;            // L + 1 + padding (elements in the breakpoint array)
-    int copies;                    // bank modes: copies per record / breakpoint element
+    int copies;                    // bank modes: copies per record element (kSmemV: per 16-byte chunk)
+    int bcopies;                   // bank modes: copies per breakpoint element (a power of two)
     int soff_breaks, soff_records; // bank modes: byte offsets of the replicated sections in shared memory
     int g0;                        // cell id of the first cell: g = floor(x*2^p) - g0
     int kstep;                     // 2^(K-1), or 0 when the grid alone is exact
-    int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit, 0 -> 32-bit
+    int first_shift;               // first[] packing: 2 -> 8-bit entries (4 per word), 1 -> 16-bit, 0 -> 32-bit;
+                                   // 3 -> no first[]: the section holds the rank words of rank_mode bit 2
     int rank_mode;                 // bit 0: leaf = rank in cont_mask of the coarse cell (no table read);
-                                   // bit 1: rec[] holds one record per COARSE CELL (n_records of them)
+                                   // bit 1: rec[] holds one record per COARSE CELL (n_records of them);
+                                   // bit 2: leaf = rank from one 32-bit word per 16 coarse cells
+                                   //        (prefix count << 16 | continuation bits), see Lookup::rank16_guess
     int n_records;                 // records in rec[]: L, or the coarse cell count in rank_mode 2
     unsigned div_mul, div_shift;   // coarse cell = (fine cell * div_mul) >> div_shift  (exact / q)
     unsigned div_add;              // -g0 * div_mul (mod 2^32): folds the "- g0" into the multiply
@@ -154,7 +166,7 @@ __host__ __device__ constexpr int rec_stride_global(int basis, int order, int el
 __host__ __device__ constexpr int rec_stride_packed(int order) { return ((order + 2) | 1); }
 template <int BASIS, int ORDER, typename T, int MODE>
 __host__ __device__ constexpr int rec_stride_for() {
-    return MODE == kGlobal ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
+    return (MODE == kGlobal || MODE == kSmemV) ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
                            : (mode_packed_hdr(MODE) ? rec_stride_packed(ORDER)
                                                     : (mode_uniform_hdr(MODE) ? rec_stride(kMono, ORDER) : rec_stride(BASIS, ORDER)));
 }
@@ -200,8 +212,8 @@ template <typename T> struct Lookup {
     // bank modes: breaks[] lives at soff_breaks, `copies` copies per element, lane l reads copy l
     __device__ __forceinline__ void use_replicated_breaks(const TableView& tv, const unsigned char* base) {
         bbase = base + tv.soff_breaks;
-        bunit_log2 = ((sizeof(T) == 4) ? 2 : 3) + (31 - __clz(tv.copies));
-        blane = (int)(threadIdx.x & (tv.copies - 1)) * (int)sizeof(T);
+        bunit_log2 = ((sizeof(T) == 4) ? 2 : 3) + (31 - __clz(tv.bcopies));
+        blane = (int)(threadIdx.x & (tv.bcopies - 1)) * (int)sizeof(T);
     }
     // fine cell of x relative to the first cell, clamped to [0, G)
     __device__ __forceinline__ int cell(T x) const {
@@ -239,6 +251,19 @@ template <typename T> struct Lookup {
         AI_CHECK(i >= 0 && i <= lmax);
         return i;
     }
+    // Dyadic tables with more than 32 coarse cells: the same rank from memory, ONE 32-bit word per
+    // 16 coarse cells = (continuation bits set in all earlier words) << 16 | this word's 16
+    // continuation bits.  Up to 512 cells the words sit in 32 different banks (lanes on the same
+    // word are a broadcast): one conflict-free wavefront, where random reads of a 16-bit first[]
+    // table of 512 entries cost ~3.5.  Verified on the host for every fine cell.
+    __device__ __forceinline__ int rank16_guess(T x) const {
+        const unsigned c = coarse_cell(x);
+        const unsigned w = reinterpret_cast<const unsigned*>(first)[c >> 4];
+        const unsigned upto = (2u << (c & 15u)) - 1u;            // bits 0..(c & 15) of this word
+        const int i = (int)c - (int)(w >> 16) - __popc(w & upto & 0xffffu);
+        AI_CHECK(i >= 0 && i <= lmax);
+        return i;
+    }
     // RECORD index of N points held in registers: the leaf ordinal, except for tables whose
     // records are stored once per coarse cell (rank_mode 2: at most 32 / 16 cells), where the
     // coarse cell itself addresses the record and the rank (shift, mask, popc, subtract) is not
@@ -259,6 +284,11 @@ template <typename T> struct Lookup {
         if (rank_mode & 1) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = rank_guess(x[e]);
+            return;
+        }
+        if (rank_mode & 4) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) i[e] = rank16_guess(x[e]);
             return;
         }
         if (fshift == 2) {
@@ -363,6 +393,25 @@ template <int BASIS, int ORDER, typename T> struct Record {
     __device__ __forceinline__ void load_strided(const T* __restrict__ rec, int stride) {
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = rec[k * stride];
+    }
+    // kSmemV: 16-byte chunk q of this lane's copy sits kVecCopies chunks after chunk q - 1
+    __device__ __forceinline__ void load_vec_smem(const T* __restrict__ rec) {
+        constexpr int PER = 16 / (int)sizeof(T);
+        constexpr int NV = (N + PER - 1) / PER;
+        const int4* p = reinterpret_cast<const int4*>(rec);
+        T buf[NV * PER];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int4 w = p[q * kVecCopies];
+            if constexpr (sizeof(T) == 4) {
+                buf[4 * q] = __int_as_float(w.x); buf[4 * q + 1] = __int_as_float(w.y);
+                buf[4 * q + 2] = __int_as_float(w.z); buf[4 * q + 3] = __int_as_float(w.w);
+            } else {
+                buf[2 * q] = __hiloint2double(w.y, w.x); buf[2 * q + 1] = __hiloint2double(w.w, w.z);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = buf[k];
     }
     // 16-byte aligned record in global memory: 128-bit read-only loads
     __device__ __forceinline__ void load_vec(const T* __restrict__ rec) {
@@ -560,14 +609,23 @@ __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, 
         const int4* src = reinterpret_cast<const int4*>(tv.image);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int k = threadIdx.x; k < tv.off_breaks / 16; k += blockDim.x) dst[k] = __ldg(src + k);
-        const int cp = (MODE == kSmemBankN) ? tv.copies : Copies<T, MODE>::value;
-        const int sh = 31 - __clz(cp);
+        const int bsh = 31 - __clz(tv.bcopies);
         const T* bsrc = reinterpret_cast<const T*>(tv.image + tv.off_breaks);
         T* bdst = reinterpret_cast<T*>(smem + tv.soff_breaks);
-        for (int k = threadIdx.x; k < tv.n_breaks_elems * cp; k += blockDim.x) bdst[k] = __ldg(bsrc + (k >> sh));
-        const T* rsrc = reinterpret_cast<const T*>(tv.image + tv.off_records);
-        T* rdst = reinterpret_cast<T*>(smem + tv.soff_records);
-        for (int k = threadIdx.x; k < tv.n_records_elems * cp; k += blockDim.x) rdst[k] = __ldg(rsrc + (k >> sh));
+        for (int k = threadIdx.x; k < (tv.n_breaks_elems << bsh); k += blockDim.x) bdst[k] = __ldg(bsrc + (k >> bsh));
+        if constexpr (MODE == kSmemV) {
+            // every 16-byte chunk of every record written kVecCopies times, chunk-interleaved
+            const int4* rsrc = reinterpret_cast<const int4*>(tv.image + tv.off_records);
+            int4* rdst = reinterpret_cast<int4*>(smem + tv.soff_records);
+            const int chunks = tv.n_records_elems / (16 / (int)sizeof(T));
+            for (int k = threadIdx.x; k < chunks * kVecCopies; k += blockDim.x) rdst[k] = __ldg(rsrc + k / kVecCopies);
+        } else {
+            const int cp = (MODE == kSmemBankN) ? tv.copies : Copies<T, MODE>::value;
+            const int sh = 31 - __clz(cp);
+            const T* rsrc = reinterpret_cast<const T*>(tv.image + tv.off_records);
+            T* rdst = reinterpret_cast<T*>(smem + tv.soff_records);
+            for (int k = threadIdx.x; k < tv.n_records_elems * cp; k += blockDim.x) rdst[k] = __ldg(rsrc + (k >> sh));
+        }
         __syncthreads();
         return smem;
     }
@@ -590,13 +648,13 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     constexpr bool VEC = (MODE == kGlobal);                        // 128-bit record loads
     constexpr bool PK = mode_packed_hdr(MODE);                     // one-element record header
     // copies per record element: compile-time except in kSmemBankN
-    const int cp = (MODE == kSmemBankN) ? tv.copies : Copies<T, MODE>::value;
+    const int cp = (MODE == kSmemBankN) ? tv.copies : (MODE == kSmemV ? kVecCopies : Copies<T, MODE>::value);
     // record stride in elements (kSmemBankN: packed or unpacked header, decided per table)
     const int R = ((MODE == kSmemBankN && Record<BASIS, ORDER, T>::HDR == 2 && tv.s0_hi)
                        ? rec_stride_packed(ORDER) : rec_stride_for<BASIS, ORDER, T, MODE>()) * cp;
-    // bank-private layout: lane l reads copy l mod cp of every element
+    // bank-private layout: lane l reads copy l mod cp of every element (kSmemV: of every 16-byte chunk)
     const T* records = reinterpret_cast<const T*>(base + (kBank ? tv.soff_records : tv.off_records))
-                       + (threadIdx.x & (cp - 1));
+                       + (threadIdx.x & (cp - 1)) * (MODE == kSmemV ? 16 / (int)sizeof(T) : 1);
     if constexpr (kBank) lk.use_replicated_breaks(tv, base);
     const T inv_order = (T)tv.inv_order;
 
@@ -608,6 +666,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
         } else {
             const T* p = records + leaf * R;
             if constexpr (VEC) r.load_vec(p);
+            else if constexpr (MODE == kSmemV) r.load_vec_smem(p);
             else if constexpr (PK) r.template load_packed<Copies<T, MODE>::value>(p, tv.s0_hi, tv.s0_lo);
             else if constexpr (mode_uniform_hdr(MODE))
                 r.template load_uniform<Copies<T, MODE>::value>(p, leaf, (T)tv.u_w, (T)tv.u_lb, (T)tv.u_s);

@@ -19,7 +19,7 @@ import types
 import numpy as np
 import numpy.linalg as la
 
-from . import generate, tables
+from . import _cabi, generate, tables
 
 FLAG = "gpu find_error"
 
@@ -27,7 +27,11 @@ FLAG = "gpu find_error"
 def _gpu_eval_single_leaf(basis, order, dtype, coeff, a, b, x):
     dt = np.dtype(dtype)
     flat = tables.FlatTable(basis, int(order), dt, np.array([a, b], dtype=dt), np.asarray(coeff, dtype=dt))
-    return generate.run(np.asarray(x, dtype=dt), tables.DeviceTable(flat, generate._backend().cuda.current_device()))
+    tab = tables.DeviceTable(flat, generate._backend().cuda.current_device())
+    try:
+        return generate.run(np.asarray(x, dtype=dt), tab)
+    finally:
+        tab.close()
 
 
 def accelerate(fitter):
@@ -44,11 +48,13 @@ def accelerate(fitter):
             full_x = np.linspace(lb, ub, int(5e3 * (ub - lb) + 10), dtype=self.dtype)
             cache[key] = la.norm(self.function(full_x), np.inf)
         x = np.linspace(a, b, n, dtype=self.dtype)
-        try:
-            approx = _gpu_eval_single_leaf(self.basis, order, self.dtype, coeff, a, b, x)
-        except Exception:
-            # degenerate node (a == b in the table dtype, order outside the kernel range ...)
+        # The two documented degenerate nodes go to the reference's own find_error: an interval that
+        # is empty in the table dtype (no table can be built on it) and an order the kernels are not
+        # instantiated for.  Everything else -- a missing library, a CUDA error, a shape bug -- raises.
+        dt = np.dtype(self.dtype).type
+        if not (dt(a) < dt(b)) or not (0 <= int(order) <= _cabi.MAX_ORDER):
             return original(coeff, a, b, order)
+        approx = _gpu_eval_single_leaf(self.basis, order, self.dtype, coeff, a, b, x)
         max_abs_err = la.norm(approx - self.function(x), np.inf)
         return max_abs_err / cache[key]
 

@@ -89,15 +89,31 @@ def gen_ispc(ap):
 
 # ------------------------------------------------------------------ device tables
 class _Entry(object):
-    __slots__ = ("ref", "tables", "stamp")
+    __slots__ = ("ref", "tables", "stamp", "identity")
 
 
 _REGISTRY = {}
 
 
+def _identity(approx):
+    """Cheap per-call check that `approx` still carries the table it was staged from: the identity,
+    buffer address, shape and dtype of tree_1d plus basis and order.  The content hash (`_stamp`)
+    is only recomputed when this changes -- hashing a 10^5-leaf tree_1d costs milliseconds, more than
+    the kernel it would precede.  (A tree_1d edited IN PLACE needs generate.invalidate(approx).)"""
+    t = approx.tree_1d
+    addr = t.__array_interface__["data"][0] if isinstance(t, np.ndarray) else None
+    return (id(t), addr, getattr(t, "shape", None), str(getattr(t, "dtype", "")), str(approx.basis),
+            int(approx.max_order))
+
+
 def _stamp(approx):
     t = np.asarray(approx.tree_1d)
     return (str(approx.basis), int(approx.max_order), str(t.dtype), t.shape, hash(t.tobytes()))
+
+
+def invalidate(approx):
+    """Drop the device tables cached for `approx` (after editing its tree_1d in place)."""
+    _REGISTRY.pop(id(approx), None)
 
 
 def device_table(approx, device=None):
@@ -110,11 +126,18 @@ def device_table(approx, device=None):
         return approx
     key = id(approx)
     ent = _REGISTRY.get(key)
-    stamp = _stamp(approx)
-    if ent is None or ent.ref() is not approx or ent.stamp != stamp:
+    ident = _identity(approx)
+    if ent is not None and ent.ref() is approx and ent.identity != ident:
+        # same object, different tree_1d array: staged tables stay only if the content is the same
+        if ent.stamp == _stamp(approx):
+            ent.identity = ident
+        else:
+            ent = None
+    if ent is None or ent.ref() is not approx:
         ent = _Entry()
         ent.tables = {}
-        ent.stamp = stamp
+        ent.stamp = _stamp(approx)
+        ent.identity = ident
         try:
             ent.ref = weakref.ref(approx)
             weakref.finalize(approx, _REGISTRY.pop, key, None)
@@ -152,12 +175,25 @@ def build_code(approx, ispc=False):
     return knl, int(dev), tab
 
 
+def _device_of(torch, x):
+    """The GPU a call runs on: the device of x when x already lives on one (torch CUDA tensor or
+    any __cuda_array_interface__ object), else the current device.  The table is created (and
+    cached) per device, and the stream is taken from the same device, so pointers, table and stream
+    always agree."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return int(x.device.index)
+    elif hasattr(x, "__cuda_array_interface__"):
+        return int(torch.as_tensor(x, device="cuda").device.index)
+    return int(torch.cuda.current_device())
+
+
 def _as_device(torch, x, dtype, device):
     """-> (x_dev tensor, was_numpy).  dtype is the TABLE dtype: the reference kernel is declared
     in it (generate.py:172-174) and feeding another dtype there is undefined; we convert."""
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     if not isinstance(x, torch.Tensor) and hasattr(x, "__cuda_array_interface__"):
-        x = torch.as_tensor(x, device=device)       # cupy / numba / pycuda arrays: zero-copy view
+        x = torch.as_tensor(x, device="cuda")       # cupy / numba / pycuda arrays: zero-copy view, on ITS device
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
             return x.to(device=device, dtype=tdt).contiguous().view(-1), False
@@ -167,6 +203,9 @@ def _as_device(torch, x, dtype, device):
 
 
 def _launch(torch, tab, x_dev, y_dev):
+    if x_dev.device.index != tab.device or y_dev.device.index != tab.device:
+        raise ValueError("x / y live on cuda:%s but the table was staged on cuda:%d"
+                         % (x_dev.device.index, tab.device))
     stream = torch.cuda.current_stream(x_dev.device).cuda_stream
     tab.eval_ptr(x_dev.data_ptr(), y_dev.data_ptr(), x_dev.numel(), stream)
 
@@ -174,12 +213,12 @@ def _launch(torch, tab, x_dev, y_dev):
 def run(x, approx):
     """generate.py:158-187: build and run in one call, untimed; returns y."""
     torch = _backend()
-    dev = torch.cuda.current_device()
+    dev = _device_of(torch, x)
     tab = device_table(approx, dev)
     x_dev, was_numpy = _as_device(torch, x, tab.flat.dtype, torch.device("cuda", dev))
     y_dev = torch.empty_like(x_dev)
     _launch(torch, tab, x_dev, y_dev)
-    torch.cuda.current_stream().synchronize()
+    torch.cuda.current_stream(x_dev.device).synchronize()
     return y_dev.cpu().numpy() if was_numpy else y_dev
 
 
@@ -187,55 +226,80 @@ def run_single(x, ap):
     """generate.py:480-490: returns (seconds, y); the timed region is the kernel only
     (queue.finish(); t0; launch; queue.finish(); t1), measured here with CUDA events."""
     torch = _backend()
-    dev = torch.cuda.current_device()
+    dev = _device_of(torch, x)
     tab = device_table(ap, dev)
     x_dev, was_numpy = _as_device(torch, x, tab.flat.dtype, torch.device("cuda", dev))
     y_dev = torch.empty_like(x_dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.current_stream().synchronize()
-    e0.record()
+    stream = torch.cuda.current_stream(x_dev.device)
+    stream.synchronize()
+    e0.record(stream)
     _launch(torch, tab, x_dev, y_dev)
-    e1.record()
+    e1.record(stream)
     e1.synchronize()
     seconds = e0.elapsed_time(e1) * 1e-3
     return seconds, (y_dev.cpu().numpy() if was_numpy else y_dev)
 
 
-def run_multi(x, ap, devices=None):
-    """generate.py:493-502 (the 'multi-threaded' launch).  Here: contiguous shards of x over the
-    given GPUs of this process (default: all visible), table replicated, no collective; returns
-    (max over devices of the kernel seconds, y)."""
+def pinned_empty(n, dtype):
+    """A 1-D numpy array of n elements in page-locked host memory (ai_host_alloc).  Host arrays
+    handed to run_multi / DeviceTable.eval_host move at full PCIe speed when they are pinned;
+    pageable arrays work too (the driver stages them, at roughly half the rate)."""
+    import ctypes
+    dt = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    nbytes = max(int(n), 1) * dt.itemsize
+    _cabi.check(_cabi.lib().ai_host_alloc(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_byte * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    weakref.finalize(buf, _cabi.lib().ai_host_free, p)
+    return arr
+
+
+def run_multi(x, ap, devices=None, timing="kernel"):
+    """generate.py:493-502 (the 'multi-threaded' launch).  Here: contiguous shards of the HOST array
+    x over the given GPUs of this process (default: all visible), table replicated, no collective.
+    One worker thread per device pushes its shard through the library's pinned, chunked
+    H2D / kernel / D2H pipeline (ai_eval_host_*; the GIL is released during the call), so the copies
+    of all devices overlap.  Returns (seconds, y): seconds is the max over devices of the summed
+    kernel time (`timing="kernel"`, the reference's kernel-only convention, generate.py:484-489) or
+    the wall time of the whole call including every copy (`timing="wall"`)."""
     torch = _backend()
+    import threading
+    import time
     from . import sharding
+    if timing not in ("kernel", "wall"):
+        raise Exception("timing must be 'kernel' or 'wall'")
     if devices is None:
         devices = list(range(torch.cuda.device_count()))
-    if isinstance(x, torch.Tensor) and x.is_cuda:
-        return run_single(x, ap)
+    if (isinstance(x, torch.Tensor) and x.is_cuda) or hasattr(x, "__cuda_array_interface__"):
+        return run_single(x, ap)            # already resident on one device
     dt = tables.table_dtype(ap)
     xa = np.ascontiguousarray(np.asarray(x), dtype=dt).reshape(-1)
-    bounds = sharding.shard_bounds(xa.size, len(devices))
-    parts = []
-    for d, (lo, hi) in zip(devices, bounds):
-        with torch.cuda.device(d):
-            tab = device_table(ap, d)
-            xd = torch.from_numpy(xa[lo:hi]).to(torch.device("cuda", d))
-            yd = torch.empty_like(xd)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            parts.append((d, tab, xd, yd, e0, e1))
-    for d, tab, xd, yd, e0, e1 in parts:
-        torch.cuda.synchronize(d)
-    for d, tab, xd, yd, e0, e1 in parts:            # launch everywhere before waiting anywhere
-        with torch.cuda.device(d):
-            e0.record()
-            _launch(torch, tab, xd, yd)
-            e1.record()
-    seconds = 0.0
     out = np.empty_like(xa)
-    for (d, tab, xd, yd, e0, e1), (lo, hi) in zip(parts, bounds):
-        e1.synchronize()
-        seconds = max(seconds, e0.elapsed_time(e1) * 1e-3)
-        out[lo:hi] = yd.cpu().numpy()
-    return seconds, out
+    bounds = sharding.shard_bounds(xa.size, len(devices))
+    tabs = [device_table(ap, d) for d in devices]          # created before the clock starts
+    kernel_ms = [0.0] * len(devices)
+    errors = []
+
+    def worker(k):
+        lo, hi = bounds[k]
+        try:
+            if hi > lo:
+                _, kernel_ms[k] = tabs[k].eval_host(xa[lo:hi], out[lo:hi])
+        except Exception as e:                              # re-raised in the caller's thread
+            errors.append(e)
+
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(devices))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    wall = time.perf_counter() - t0
+    if errors:
+        raise errors[0]
+    return (wall if timing == "wall" else max(kernel_ms) * 1e-3), out
 
 
 def run_many(x, approxs):
@@ -248,7 +312,7 @@ def run_many(x, approxs):
     approxs = list(approxs)
     if not 1 <= len(approxs) <= _cabi.MAX_MULTI:
         raise Exception("run_many takes 1..%d approximations, got %d" % (_cabi.MAX_MULTI, len(approxs)))
-    dev = torch.cuda.current_device()
+    dev = _device_of(torch, x)
     tabs = [device_table(ap, dev) for ap in approxs]
     dt = tabs[0].flat.dtype
     if any(t.flat.dtype != dt for t in tabs):
@@ -258,10 +322,10 @@ def run_many(x, approxs):
     stream = torch.cuda.current_stream(x_dev.device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream.synchronize()
-    e0.record()
+    e0.record(stream)
     tables.DeviceTable.eval_multi_ptr(tabs, x_dev.data_ptr(), [y.data_ptr() for y in ys], x_dev.numel(),
                                       stream.cuda_stream)
-    e1.record()
+    e1.record(stream)
     e1.synchronize()
     seconds = e0.elapsed_time(e1) * 1e-3
     return seconds, [y.cpu().numpy() if was_numpy else y for y in ys]
@@ -270,10 +334,11 @@ def run_many(x, approxs):
 def run_index(x, approx):
     """Leaf ordinal per point (bit-exact with the reference's BST walk, approximator.py:285-290)."""
     torch = _backend()
-    dev = torch.cuda.current_device()
+    dev = _device_of(torch, x)
     tab = device_table(approx, dev)
     x_dev, was_numpy = _as_device(torch, x, tab.flat.dtype, torch.device("cuda", dev))
     idx = torch.empty(x_dev.numel(), dtype=torch.int32, device=x_dev.device)
-    tab.index_ptr(x_dev.data_ptr(), idx.data_ptr(), x_dev.numel(), torch.cuda.current_stream().cuda_stream)
-    torch.cuda.current_stream().synchronize()
+    stream = torch.cuda.current_stream(x_dev.device)
+    tab.index_ptr(x_dev.data_ptr(), idx.data_ptr(), x_dev.numel(), stream.cuda_stream)
+    stream.synchronize()
     return idx.cpu().numpy() if was_numpy else idx

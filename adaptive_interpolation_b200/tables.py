@@ -82,6 +82,45 @@ def flatten_tree_1d(tree_1d, order):
     return a, b, np.array(coef, dtype=t.dtype).reshape(len(a), n + 1)
 
 
+def flatten_tree_1d_trim(tree_1d, order):
+    """Enumerate the leaves of a `trim_data`-layout tree_1d (approximator.py:202-206, 232-233).
+
+    Nodes are stored in preorder; a leaf is [mid, self, self, c0..cn, a, b] (both links equal), an
+    inner node is [mid, left NODE index, right NODE index].  The reference's own walk reads those
+    node indices as element offsets (approximator.py:275-290), so the links cannot be followed; a
+    preorder scan visits the same leaves left to right.  Returns (a, b, coef[L, n+1])."""
+    t = np.asarray(tree_1d)
+    n = int(order)
+    a, b, coef = [], [], []
+    o, node, pending = 0, 0, []
+    while o < len(t):
+        if o + 3 > len(t):
+            raise ValueError("trim_data tree_1d ends inside node %d" % node)
+        if pending and pending[-1] == node:
+            pending.pop()
+        if t[o + 1] == t[o + 2]:
+            if o + n + 6 > len(t):
+                raise ValueError("trim_data tree_1d ends inside leaf node %d" % node)
+            coef.append(t[o + 3:o + n + 4])
+            a.append(t[o + n + 4])
+            b.append(t[o + n + 5])
+            o += n + 6
+        else:
+            if int(t[o + 1]) != node + 1:
+                raise ValueError("trim_data node %d: left child %r is not the next node" % (node, t[o + 1]))
+            pending.append(int(t[o + 2]))
+            o += 3
+        node += 1
+    if pending or 2 * len(a) - 1 != node:
+        raise ValueError("trim_data tree_1d is not a full binary tree (%d nodes, %d leaves)" % (node, len(a)))
+    a = np.array(a, dtype=t.dtype)
+    b = np.array(b, dtype=t.dtype)
+    if np.any(a[1:] != b[:-1]):
+        k = int(np.nonzero(a[1:] != b[:-1])[0][0])
+        raise ValueError("leaves %d and %d are not contiguous (%r != %r)" % (k, k + 1, b[k], a[k + 1]))
+    return a, b, np.array(coef, dtype=t.dtype).reshape(len(a), n + 1)
+
+
 def flatten_nodes(root, basis, order, dtype):
     """Flatten the fitter's raw tree (adapt.py:14-48 Tree/Node objects, node.data = [mid, coeff,
     [a, b], err], adapt.py:233 / :381) straight to a FlatTable.  This is the route for deep or
@@ -152,13 +191,13 @@ def flatten(approx):
     if isinstance(approx, FlatTable):
         return approx
     opts = list(getattr(approx, "optimizations", []) or [])
-    if "trim_data" in opts:
-        raise Exception("trim_data tables are not supported: the reference's own evaluator indexes "
-                        "that layout inconsistently (approximator.py:202-206 vs 275-290)")
     dt = table_dtype(approx)
     n = int(approx.max_order)
     tree_1d = np.asarray(approx.tree_1d, dtype=dt)          # run_test.py:242 cast
-    a, b, coef = flatten_tree_1d(tree_1d, n)
+    if "trim_data" in opts:
+        a, b, coef = flatten_tree_1d_trim(tree_1d, n)
+    else:
+        a, b, coef = flatten_tree_1d(tree_1d, n)
     ia = getattr(approx, "interval_a", None)
     if ia is not None and len(ia) == len(a):
         ib, co = approx.interval_b, approx.coeff
@@ -198,8 +237,9 @@ class DeviceTable(object):
         self._finalizer = weakref.finalize(self, L.ai_table_destroy, h)
 
     @classmethod
-    def from_tree_1d(cls, basis, order, dtype, num_levels, tree_1d, device=0):
-        """Flattening done inside the library (ai_table_create_from_tree)."""
+    def from_tree_1d(cls, basis, order, dtype, num_levels, tree_1d, device=0, layout=_cabi.TREE_LAYOUT_STANDARD):
+        """Flattening done inside the library (ai_table_create_from_tree); layout
+        _cabi.TREE_LAYOUT_TRIM for "trim_data" tables."""
         self = cls.__new__(cls)
         L = _cabi.lib()
         dt = np.dtype(dtype)
@@ -207,7 +247,7 @@ class DeviceTable(object):
         h = ctypes.c_void_p()
         _cabi.check(L.ai_table_create_from_tree(
             _cabi.BASIS_IDS[basis], int(order), _cabi.DTYPE_F32 if dt == np.float32 else _cabi.DTYPE_F64,
-            int(num_levels), 0, t.ctypes.data, len(t), int(device), ctypes.byref(h)))
+            int(num_levels), int(layout), t.ctypes.data, len(t), int(device), ctypes.byref(h)))
         self._h = h
         self.device = int(device)
         self._finalizer = weakref.finalize(self, L.ai_table_destroy, h)

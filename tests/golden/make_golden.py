@@ -299,77 +299,241 @@ def freeze(name, ap, source, func_name, rng, total=2048, clustered=False, extra_
     return meta
 
 
-def main():
-    os.makedirs(OUT, exist_ok=True)
-    for fn in os.listdir(OUT):
-        if fn.endswith(".npz"):
-            os.remove(os.path.join(OUT, fn))
-    manifest = []
-    seed = 1000
+# ---------------------------------------------------------------- job lists
+EPS64 = float(np.finfo(np.float64).eps)
 
-    # 1. every saved pickle ------------------------------------------------------------
+GEN = [
+    # name, (a, b, func, order, err, basis, adapt_type, dtype, accurate, opts)
+    ("gen__cfg1_sinsin_cheb_o3_f64", (0, 10, "sinsin", 3, 1e-6, "chebyshev", "Remez", "64", True, ["arrays", "map"])),
+    ("gen__cfg3_j0_cheb_o13_f64", (0, 20, "j0", 13, 100 * EPS64, "chebyshev", "Remez", "64", True, ["arrays", "map", "random"])),
+    ("gen__j0_mono_o5_f64", (0, 20, "j0", 5, 1e-5, "monomial", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__j0_mono_o13_f64", (0, 20, "j0", 13, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__j0_leg_o7_f32", (0, 20, "j0", 7, 1e-5, "legendre", "Trivial", "32", True, ["arrays", "map"])),
+    ("gen__j0_leg_o7_f64", (0, 20, "j0", 7, 1e-9, "legendre", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__j0_leg_o6_remez_f64", (0, 20, "j0", 6, 1e-8, "legendre", "Remez", "64", True, ["arrays", "map"])),
+    ("gen__j0_cheb_o10_f32", (0, 20, "j0", 10, 1e-6, "chebyshev", "Trivial", "32", True, ["arrays", "map"])),
+    # the reference's own accuracy/exactness tests (tests/performance_tests.py:112-162)
+    ("gen__poly4_mono_o4_f64", (-10, 10, "poly4", 4, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__poly6_mono_o6_f64", (-10, 10, "poly6", 6, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__line1_mono_o1_f64", (-10, 10, "line1", 1, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__sinsin_mono_o10_f64", (-10, 10, "sinsin", 10, 1e-6, "monomial", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__cossin_cheb_o10_f64", (-10, 10, "cossin", 10, 1e-9, "chebyshev", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__sinsin_leg_o10_f64", (-10, 10, "sinsin", 10, 1e-9, "legendre", "Trivial", "64", True, ["arrays", "map"])),
+    ("gen__sinsin_cheb_o2_f32", (-3, 3, "sinsin", 2, 1e-4, "chebyshev", "Trivial", "32", True, ["arrays", "map"])),
+]
+
+
+def matrix_jobs():
+    """One reference-fitted table for EVERY (basis, order 3..13, dtype) the kernels are specialised
+    on (BASELINE configs[4]: "32/64-bit, orders 3-13, monomial/Chebyshev/Legendre";
+    adapt.py:97-139 defines all three bases for any order; tests/performance_tests.py:132-162 sweeps
+    the bases).  Chebyshev / Legendre: J0 on [0,20]; monomial: sin(sin x) on [-2,2] (a monomial
+    basis on the raw x of [0,20] is singular at these orders, adapt.py:213-219).  All 66 construct."""
+    out = []
+    for dtype, err in (("32", 1e-5), ("64", 1e-9)):
+        for basis, short in (("chebyshev", "cheb"), ("legendre", "leg"), ("monomial", "mono")):
+            for order in range(3, 14):
+                fn, a, b = ("sinsin", -2, 2) if basis == "monomial" else ("j0", 0, 20)
+                out.append(("mx__%s_o%d_f%s" % (short, order, dtype),
+                            (a, b, fn, order, err, basis, "Trivial", dtype, True, ["arrays", "map"])))
+    return out
+
+
+# the reference's missing saved tables (/root/reference/.MISSING_LARGE_BLOBS), refitted with the
+# recipe that made them (run_test.py:458-488 save_approximations: Chebyshev, Remez, dtype 64,
+# J0 on [0,20] for approx/, [1,21] for approximations/).  The `ci` twins differ from their
+# non-`ci` twin only in the "calc intervals" flag (packed map for the ISPC variant), which also
+# caps the tree depth at 14 (adapt.py:69-72); they are refitted with that flag.
+LARGE = [
+    ("approx__64o3-p2.22044604925e-14", (0, 20, 3, 2.22044604925e-14, ["arrays", "map", "random"])),
+    ("approx__64o3-p2.22044604925e-15", (0, 20, 3, 2.22044604925e-15, ["arrays", "map", "random"])),
+    ("approx__ci64o3-p2.22044604925e-14", (0, 20, 3, 2.22044604925e-14, ["arrays", "map", "calc intervals", "random"])),
+    ("approx__ci64o3-p2.22044604925e-15", (0, 20, 3, 2.22044604925e-15, ["arrays", "map", "calc intervals", "random"])),
+    ("approximations__64o3-p2.22044604925e-14", (1, 21, 3, 2.22044604925e-14, ["arrays", "map", "calc intervals", "random"])),
+]
+
+
+def fit(a, b, fname, order, err, basis, atype, dtype, acc, opts):
+    with linspace_int_shim(), quiet():
+        return ref_api.make_interpolant(a, b, FUNCS[fname], order, err, basis, atype, dtype, acc, list(opts))
+
+
+def job_pickle(d, fn, seed):
+    ap = ref_api.load_from_file(os.path.join(REF, d, fn))
+    perr = float(fn.split("-p")[1])
+    return freeze("%s__%s" % (d, fn), ap, "pickle:%s/%s" % (d, fn), "j0", np.random.default_rng(seed),
+                  allowed_error=perr)
+
+
+def job_gen(name, spec, seed, total=2048):
+    a, b, fname, order, err, basis, atype, dtype, acc, opts = spec
+    try:
+        ap = fit(*spec)
+    except Exception as e:                      # a fit the reference cannot produce
+        print("SKIP %s: %s: %s" % (name, type(e).__name__, str(e)[:80]))
+        return None
+    extra = None
+    if name.startswith("gen__cfg1"):
+        # BASELINE config 1: 2**20 linspace points; freeze a strided sample of them
+        extra = np.linspace(0, 10, 2**20, endpoint=False)[::128]
+    return freeze(name, ap, "make_interpolant%r" % (spec,), fname, np.random.default_rng(seed), total=total,
+                  extra_x=extra, allowed_error=err)
+
+
+def job_cfg4(name, dtype, err, seed):
+    with linspace_int_shim(), quiet():
+        it = ref_adapt.Interpolant(f1, 7, err, "legendre", dtype, False)
+        it.run_adapt(0, 10, "Trivial")
+    ap = approximator_from_raw_tree(it)
+    return freeze(name, ap, "Interpolant(f1,7,%g,'legendre','%s',False).run_adapt(0,10,'Trivial')" % (err, dtype),
+                  "f1", np.random.default_rng(seed), total=6144, clustered=True, allowed_error=err)
+
+
+def job_large(name, spec, seed):
+    """A missing saved table, refitted by the reference's fitter and flattened from its raw tree
+    (the Approximator constructor trips approximator.py:178 on these; with
+    "calc intervals" the fitter itself gives up past depth 14 -- recorded as a SKIP)."""
+    a, b, order, err, opts = spec
+    sys.setrecursionlimit(200000)
+    try:
+        with linspace_int_shim(), quiet():
+            it = ref_adapt.Interpolant(f, order, err, "chebyshev", "64", True, optimizations=list(opts))
+            it.run_adapt(a, b, "Remez")
+    except Exception as e:
+        print("SKIP %s: %s: %s" % (name, type(e).__name__, str(e)[:80].replace("\n", " ")))
+        return None
+    ap = approximator_from_raw_tree(it)
+    ap.optimizations = list(opts)
+    return freeze(name, ap, "refit of .MISSING_LARGE_BLOBS: Interpolant(j0,%d,%g,'chebyshev','64',True,%r).run_adapt(%g,%g,'Remez')"
+                  % (order, err, opts, a, b), "j0", np.random.default_rng(seed), total=8192, allowed_error=err)
+
+
+def job_trim(name, seed):
+    """The `trim_data` tree layout (approximator.py:202-206,232-233): leaves
+    [mid, self, self, c0..cn, a, b], inner nodes [mid, left NODE index, right NODE index].  The
+    reference's tree_1d walk (approximator.py:275-290) reads those node indices as element offsets,
+    so Approximator.evaluate is not usable on it; y_ref is Approximator.evaluate_tree
+    (approximator.py:244-271), the walk over the node objects of the same tree (fp64 table: the
+    node coefficients ARE the tree_1d values).  The BST leaf is restated on the node objects."""
+    spec = (0, 20, "j0", 6, 1e-6, "chebyshev", "Remez", "64", True, ["arrays", "map", "trim_data"])
+    ap = fit(*spec)
+    rng = np.random.default_rng(seed)
+    n = int(ap.max_order)
+    dt = np.float64
+    a = np.asarray(ap.interval_a, dtype=dt)
+    b = np.asarray(ap.interval_b, dtype=dt)
+    breaks = np.concatenate([a, b[-1:]])
+    x = make_points(ap, breaks, rng, 2048)
+    with np.errstate(all="ignore"):
+        y_ref = np.array(ap.evaluate_tree(x), dtype=dt)
+        f_true = np.asarray(FUNCS["j0"](x.astype(np.float64)), dtype=np.float64)
+    idx_ref = np.empty(len(x), dtype=np.int32)
+    leaves = []
+
+    def walk(nd):
+        if nd.left == 0 and nd.right == 0:
+            leaves.append(nd)
+        else:
+            walk(nd.left)
+            walk(nd.right)
+    walk(ap.tree.root)
+    pos = {id(nd): k for k, nd in enumerate(leaves)}
+    for k, xn in enumerate(x):
+        node = ap.tree.root
+        for _ in range(1, int(ap.num_levels)):                 # approximator.py:250-256
+            if node.data[0] > xn:
+                node = node.left if (node.left != 0) else node
+            else:
+                node = node.right if (node.right != 0) else node
+        idx_ref[k] = pos[id(node)]
+    dom = np.linspace(0.0, 20.0, 200001)
+    meta = dict(name=name, source="make_interpolant%r; y_ref = evaluate_tree" % (spec,), function="j0",
+                basis="chebyshev", order=n, num_levels=int(ap.num_levels), dtype="float64",
+                lower_bound=0.0, upper_bound=20.0, optimizations=list(ap.optimizations),
+                n_leaves=len(leaves), allowed_error=1e-6, fmax=float(np.max(np.abs(f(dom)))),
+                dtype_name="double", n_points=int(len(x)))
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), meta=np.array(json.dumps(meta)),
+        tree_1d=np.asarray(ap.tree_1d, dtype=dt), interval_a=a, interval_b=b,
+        coeff=np.asarray(ap.coeff, dtype=np.float64), map=np.asarray(ap.map).astype(np.int64),
+        cmap=np.asarray(ap.cmap).astype(np.int64), x=x, y_ref=y_ref, idx_ref=idx_ref, f_true=f_true)
+    print("%-34s trim_data layout, L=%d, tree_1d %d elements" % (name, len(leaves), len(ap.tree_1d)))
+    return meta
+
+
+def all_jobs():
+    """[(name, thunk)] in a fixed order; every job has its own fixed seed."""
+    jobs = []
+    seed = 1000
     for d in ("approx", "approximations"):
         for fn in sorted(os.listdir(os.path.join(REF, d))):
-            ap = ref_api.load_from_file(os.path.join(REF, d, fn))
-            perr = float(fn.split("-p")[1])
-            name = "%s__%s" % (d, fn)
             seed += 1
-            manifest.append(freeze(name, ap, "pickle:%s/%s" % (d, fn), "j0",
-                                   np.random.default_rng(seed), allowed_error=perr))
-
-    # 2. tables the BASELINE configs need, made by the reference's own fitter -------------
-    eps64 = float(np.finfo(np.float64).eps)
-    gen = [
-        # name, (a, b, func, order, err, basis, adapt_type, dtype, accurate, opts)
-        ("gen__cfg1_sinsin_cheb_o3_f64", (0, 10, "sinsin", 3, 1e-6, "chebyshev", "Remez", "64", True, ["arrays", "map"])),
-        ("gen__cfg3_j0_cheb_o13_f64", (0, 20, "j0", 13, 100 * eps64, "chebyshev", "Remez", "64", True, ["arrays", "map", "random"])),
-        ("gen__j0_mono_o5_f64", (0, 20, "j0", 5, 1e-5, "monomial", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__j0_mono_o13_f64", (0, 20, "j0", 13, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__j0_leg_o7_f32", (0, 20, "j0", 7, 1e-5, "legendre", "Trivial", "32", True, ["arrays", "map"])),
-        ("gen__j0_leg_o7_f64", (0, 20, "j0", 7, 1e-9, "legendre", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__j0_leg_o6_remez_f64", (0, 20, "j0", 6, 1e-8, "legendre", "Remez", "64", True, ["arrays", "map"])),
-        ("gen__j0_cheb_o10_f32", (0, 20, "j0", 10, 1e-6, "chebyshev", "Trivial", "32", True, ["arrays", "map"])),
-        # the reference's own accuracy/exactness tests (tests/performance_tests.py:112-162)
-        ("gen__poly4_mono_o4_f64", (-10, 10, "poly4", 4, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__poly6_mono_o6_f64", (-10, 10, "poly6", 6, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__line1_mono_o1_f64", (-10, 10, "line1", 1, 1e-9, "monomial", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__sinsin_mono_o10_f64", (-10, 10, "sinsin", 10, 1e-6, "monomial", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__cossin_cheb_o10_f64", (-10, 10, "cossin", 10, 1e-9, "chebyshev", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__sinsin_leg_o10_f64", (-10, 10, "sinsin", 10, 1e-9, "legendre", "Trivial", "64", True, ["arrays", "map"])),
-        ("gen__sinsin_cheb_o2_f32", (-3, 3, "sinsin", 2, 1e-4, "chebyshev", "Trivial", "32", True, ["arrays", "map"])),
-    ]
-    for name, (a, b, fname, order, err, basis, atype, dtype, acc, opts) in gen:
+            jobs.append(("%s__%s" % (d, fn), lambda d=d, fn=fn, seed=seed: job_pickle(d, fn, seed)))
+    for name, spec in GEN:
         seed += 1
-        try:
-            with linspace_int_shim(), quiet():
-                ap = ref_api.make_interpolant(a, b, FUNCS[fname], order, err, basis, atype,
-                                              dtype, acc, list(opts))
-        except Exception as e:                      # a fit the reference cannot produce
-            print("SKIP %s: %s: %s" % (name, type(e).__name__, str(e)[:80]))
-            continue
-        extra = None
-        total = 2048
-        if name.startswith("gen__cfg1"):
-            # BASELINE config 1: 2**20 linspace points; freeze a strided sample of them
-            extra = np.linspace(0, 10, 2**20, endpoint=False)[::128]
-        manifest.append(freeze(name, ap, "make_interpolant%r" % ((a, b, fname, order, err, basis, atype, dtype, acc, opts),),
-                               fname, np.random.default_rng(seed), total=total, extra_x=extra,
-                               allowed_error=err))
-
-    # 3. BASELINE config 4: deep, skewed trees (piecewise f1, Legendre order 7) -------------
+        jobs.append((name, lambda name=name, spec=spec, seed=seed: job_gen(name, spec, seed)))
     for name, dtype, err in (("gen__cfg4_f1_leg_o7_f32", "32", 1e-4), ("gen__cfg4_f1_leg_o7_f64", "64", 1e-6)):
         seed += 1
-        with linspace_int_shim(), quiet():
-            it = ref_adapt.Interpolant(f1, 7, err, "legendre", dtype, False)
-            it.run_adapt(0, 10, "Trivial")
-        ap = approximator_from_raw_tree(it)
-        manifest.append(freeze(name, ap, "Interpolant(f1,7,%g,'legendre','%s',False).run_adapt(0,10,'Trivial')" % (err, dtype),
-                               "f1", np.random.default_rng(seed), total=6144, clustered=True,
-                               allowed_error=err))
+        jobs.append((name, lambda name=name, dtype=dtype, err=err, seed=seed: job_cfg4(name, dtype, err, seed)))
+    seed = 2000
+    for name, spec in matrix_jobs():
+        seed += 1
+        jobs.append((name, lambda name=name, spec=spec, seed=seed: job_gen(name, spec, seed, total=1024)))
+    jobs.append(("trim__j0_cheb_o6_f64", lambda: job_trim("trim__j0_cheb_o6_f64", 3001)))
+    seed = 4000
+    for name, spec in LARGE:
+        seed += 1
+        jobs.append(("large__" + name, lambda name=name, spec=spec, seed=seed: job_large("large__" + name, spec, seed)))
+    return jobs
 
-    with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
-        json.dump(manifest, fh, indent=1)
-    print("wrote %d tables" % len(manifest))
+
+def _run_job_by_name(name):
+    return dict(all_jobs())[name]()
+
+
+def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None,
+                    help="regenerate only the tables whose name starts with one of these prefixes "
+                         "(the others and their MANIFEST entries are kept)")
+    ap.add_argument("--list", action="store_true")
+    ap.add_argument("--jobs", type=int, default=1, help="worker processes (every job has its own fixed seed)")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    jobs = all_jobs()
+    if args.list:
+        print("\n".join(n for n, _ in jobs))
+        return
+    mpath = os.path.join(HERE, "MANIFEST.json")
+    manifest = {}
+    if args.only is not None and os.path.exists(mpath):
+        with open(mpath) as fh:
+            manifest = {m["name"]: m for m in json.load(fh)}
+    selected = [(n, j) for n, j in jobs if args.only is None or any(n.startswith(p) for p in args.only)]
+    if args.only is None:
+        for fn in os.listdir(OUT):
+            if fn.endswith(".npz"):
+                os.remove(os.path.join(OUT, fn))
+    for name, _ in selected:
+        path = os.path.join(OUT, name + ".npz")
+        if os.path.exists(path):
+            os.remove(path)
+        manifest.pop(name, None)
+    if args.jobs > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(args.jobs) as pool:
+            metas = pool.map(_run_job_by_name, [n for n, _ in selected], chunksize=1)
+    else:
+        metas = [job() for _, job in selected]
+    for (name, _), meta in zip(selected, metas):
+        if meta is not None:
+            manifest[name] = meta
+    order = {n: k for k, (n, _) in enumerate(jobs)}
+    out = sorted(manifest.values(), key=lambda m: order.get(m["name"], 1 << 30))
+    with open(mpath, "w") as fh:
+        json.dump(out, fh, indent=1)
+    print("wrote %d tables (%d in the manifest)" % (len(selected), len(out)))
 
 
 if __name__ == "__main__":

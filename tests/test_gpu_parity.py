@@ -162,19 +162,27 @@ def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 9])
 def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
-    """Packed shared memory / bank-private shared memory (full or partial replication) / global
-    (L2-resident) / two-leaf select from the kernel parameters: same leaf, same arithmetic, so
-    identical indices and value bits on every table."""
+    """Packed shared memory / bank-private shared memory (full or partial replication) / eight
+    128-bit copies / global (L2-resident) / two-leaf select from the kernel parameters: same leaf,
+    same arithmetic, so identical indices and value bits on every table."""
     g = golden(name)
-    want_y = gpu_eval(dev_table(name), g.x)
+    tab0 = dev_table(name)
+    want_y = gpu_eval(tab0, g.x)
     monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
     tab = dev_table(name)
     info = tab.info()
+    if tab0.info()["residency"] == 2 and mode != 2:
+        assert info["residency"] == 2
+        pytest.skip("table larger than shared memory: L2-resident whatever is asked for")
     if mode == 4 and info["n_leaves"] > 2:
         assert info["residency"] != 4
         pytest.skip("select mode serves tables with at most two leaves")
+    if mode == 9 and info["residency"] != 9:
+        esz = 4 if g.dtype == np.float32 else 8
+        assert info["n_leaves"] * (g.max_order + 3) * esz * 8 > 200 * 1024 or info["cell_records"]
+        pytest.skip("table too large for eight copies")
     if mode == 1 and info["residency"] != 1:
         # 32 (16) copies of the records do not fit in 227 KB: the library keeps its own choice
         assert info["n_leaves"] * info["record_stride"] * 128 + info["image_bytes"] > 200 * 1024
@@ -346,12 +354,17 @@ def test_lookup_exact_on_random_tables(kind, dtype):
     # deterministic by default; AI_TEST_SEED=<n> explores other tables (tools/gpu_round_check.sh runs a few)
     kinds = ["dyadic", "random", "huge", "tiny", "clustered", "uniform"]
     rng = np.random.default_rng([kinds.index(kind), np.dtype(dtype).itemsize, int(os.environ.get("AI_TEST_SEED", "0"))])
-    seen = set()
+    seen, seen_shapes = set(), set()
     for trial in range(16):
         b = _random_breaks(rng, dtype, kind)
         L = len(b) - 1
-        coef = rng.standard_normal((L, 4)).astype(dtype)
-        tab = tables.DeviceTable(tables.FlatTable("chebyshev", 3, dtype, b, coef), 0)
+        # basis and order drawn per table (the monomial basis works on the raw x: keep it to
+        # breakpoints of moderate magnitude so x**order stays finite)
+        basis = str(rng.choice(["chebyshev", "legendre", "monomial"] if kind not in ("huge", "tiny")
+                               and float(np.max(np.abs(b))) < 64 else ["chebyshev", "legendre"]))
+        order = int(rng.integers(0, 14))
+        coef = rng.standard_normal((L, order + 1)).astype(dtype)
+        tab = tables.DeviceTable(tables.FlatTable(basis, order, dtype, b, coef), 0)
         info = tab.info()
         seen.add((info["lookup_mode"], info["residency"], info["grid_log2_scale"] < 0, info["header_packed"],
                   info["cell_records"]))
@@ -368,11 +381,14 @@ def test_lookup_exact_on_random_tables(kind, dtype):
         # and the values on the in-domain points agree with the oracle
         xin = x[np.isfinite(x) & (x >= b[0]) & (x < b[-1])]
         y = gpu_eval(tab, xin)
-        y_o = oracle_np.evaluate(b, coef, "chebyshev", 3, xin)
-        scale = oracle_np.error_scale(b, coef, "chebyshev", 3, xin)
+        y_o = oracle_np.evaluate(b, coef, basis, order, xin)
+        scale = oracle_np.error_scale(b, coef, basis, order, xin)
         ok = np.isfinite(scale)
-        assert np.all(np.abs(y[ok].astype(np.float64) - y_o[ok]) <= value_tolerance(dtype, scale[ok], GPU_ULPS))
-    report(test="random_tables", kind=kind, dtype=np.dtype(dtype).name, modes=sorted(map(list, seen)))
+        assert np.all(np.abs(y[ok].astype(np.float64) - y_o[ok]) <= value_tolerance(dtype, scale[ok], GPU_ULPS)), \
+            (kind, trial, basis, order, info)
+        seen_shapes.add((basis, order))
+    report(test="random_tables", kind=kind, dtype=np.dtype(dtype).name, modes=sorted(map(list, seen)),
+           shapes=sorted(map(list, seen_shapes)))
 
 
 def test_residency_selection():
@@ -383,9 +399,12 @@ def test_residency_selection():
     assert res["approx__32o3-p1.19209289551e-06"]["residency"] == 1           # 62 leaves, fp32
     assert res["approx__64o7-p2.22044604925e-14"]["residency"] == 1           # 64 leaves, fp64
     assert res["approx__64o6-p1.19209289551e-06"]["residency"] == 0           # 15 leaves, fp64
-    assert res["approximations__64o5-p2.22044604925e-14"]["residency"] == 3   # 429 leaves: partial copies
-    assert res["approximations__64o5-p2.22044604925e-14"]["bank_copies"] in (2, 4, 8)
-    assert res["gen__cfg4_f1_leg_o7_f64"]["residency"] == 0                   # too big for 16 copies, has a search
+    assert res["approximations__64o5-p2.22044604925e-14"]["residency"] == 9   # 429 leaves: 8 copies, 128-bit loads
+    assert res["approximations__64o5-p2.22044604925e-14"]["bank_copies"] == 8
+    assert res["gen__cfg4_f1_leg_o7_f64"]["residency"] == 9                   # too big for 16 copies: 8 x 128-bit
+    for name, info in res.items():
+        if name.startswith("large__"):
+            assert info["residency"] == 2 and info["n_leaves"] > 4096, (name, info)   # L2-resident
     for name, info in res.items():
         assert info["smem_bytes"] <= 227 * 1024
 
@@ -404,7 +423,7 @@ def test_saved_tables_need_no_search():
     for name in SAVED:
         info = dev_table(name).info()
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1, 3, 4)
+        assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1, 3, 4, 9)
     for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
         assert dev_table(name).info()["search_steps"] >= 1
 
@@ -464,6 +483,38 @@ def test_create_from_tree_equals_create():
         assert (i1["grid_cells"], i1["search_steps"]) == (i2["grid_cells"], i2["search_steps"])
 
 
+def test_create_from_trim_data_tree():
+    """ai_table_create_from_tree(layout = AI_TREE_LAYOUT_TRIM): the library's preorder scan of a
+    trim_data tree_1d (approximator.py:202-206,232-233) gives the table the host flattening gives,
+    and malformed arrays are rejected with AI_ERR_TABLE."""
+    g = golden("trim__j0_cheb_o6_f64")
+    t1 = dev_table("trim__j0_cheb_o6_f64")
+    t2 = tables.DeviceTable.from_tree_1d(g.basis, g.max_order, g.dtype, g.num_levels, g.tree_1d,
+                                         layout=_cabi.TREE_LAYOUT_TRIM)
+    assert np.array_equal(t1.flat.breaks, t2.flat.breaks) and np.array_equal(t1.flat.coef, t2.flat.coef)
+    assert np.array_equal(gpu_eval(t1, g.x), gpu_eval(t2, g.x), equal_nan=True)
+    assert np.array_equal(gpu_index(t2, g.x), g.idx_ref)
+    bad = np.asarray(g.tree_1d).copy()
+    bad[1] = 7.0
+    for arr in (bad, np.asarray(g.tree_1d)[:-2]):
+        with pytest.raises(_cabi.AiError) as ei:
+            tables.DeviceTable.from_tree_1d(g.basis, g.max_order, g.dtype, g.num_levels, arr,
+                                            layout=_cabi.TREE_LAYOUT_TRIM)
+        assert ei.value.code == 2
+
+
+def test_oversized_leaf_count_is_an_error_not_a_crash():
+    """A nonsensical n_leaves must come back as a status code (no std::bad_alloc across the C ABI)."""
+    L = _cabi.lib()
+    h = ctypes.c_void_p()
+    one = np.zeros(4, dtype=np.float64)
+    rc = L.ai_table_create(0, 3, 1, 1 << 40, one.ctypes.data, one.ctypes.data, 0, ctypes.byref(h))
+    assert rc == 4 and not h.value and b"leaves" in L.ai_last_error()
+    info = _cabi.TableInfo()
+    rc = L.ai_table_plan(0, 3, 1, 1 << 40, one.ctypes.data, one.ctypes.data, 0, ctypes.byref(info))
+    assert rc == 4
+
+
 # ------------------------------------------------------------------ host-buffer entry point
 @pytest.mark.parametrize("name,n", [("approx__32o6-p1.19209289551e-06", (1 << 25) + 12345),
                                     ("approx__64o7-p2.22044604925e-14", (1 << 23) + 77),
@@ -490,10 +541,12 @@ def test_eval_host_pipeline(name, n):
 
 def test_eval_sum_variant():
     """The reference's no-"output" kernel variant (generate.py:392-394): y reduced, not stored."""
-    for name in ("approx__32o6-p1.19209289551e-06", "gen__cfg3_j0_cheb_o13_f64"):
+    for name in ("approx__32o6-p1.19209289551e-06", "gen__cfg3_j0_cheb_o13_f64",
+                 "approximations__64o5-p2.22044604925e-14",          # eight-copy layout: reduces from the global image
+                 "large__approx__64o3-p2.22044604925e-14"):          # L2-resident
         g = golden(name)
         tab = dev_table(name)
-        x = np.random.default_rng(9).uniform(0, 20, 1 << 20).astype(g.dtype)
+        x = np.random.default_rng(9).uniform(float(g.lower_bound), float(g.upper_bound), 1 << 20).astype(g.dtype)
         y = gpu_eval(tab, x).astype(np.float64)
         xd = to_dev(x)
         res = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -554,6 +607,68 @@ def test_python_surface_matches_reference_calls():
     # nothing un-picklable was left on the object
     import pickle
     pickle.dumps(ap)
+
+
+def test_run_multi_uses_the_pinned_pipeline_and_reports_wall_time():
+    """generate.run_multi (generate.py:493-502): host array in, host array out, one worker thread
+    per visible GPU through ai_eval_host_*; pinned input from generate.pinned_empty."""
+    g = golden("approx__32o6-p1.19209289551e-06")
+    ap = app.Approximator.from_record(g)
+    n = (1 << 22) + 3
+    x = generate.pinned_empty(n, np.float32)
+    x[:] = np.random.default_rng(5).uniform(0, 20, n).astype(np.float32)
+    want = gpu_eval(dev_table(g.name), x)
+    sec_k, out = generate.run_multi(x, ap)
+    assert sec_k > 0 and np.array_equal(out, want)
+    sec_w, out = generate.run_multi(x, ap, timing="wall")
+    assert sec_w >= sec_k * 0.5 and np.array_equal(out, want)
+    sec_1, out = generate.run_multi(x, ap, devices=[0])
+    assert np.array_equal(out, want)
+    with pytest.raises(Exception):
+        generate.run_multi(x, ap, timing="cpu")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_input_on_another_device_than_the_current_one():
+    """A CUDA tensor is evaluated where it lives: table, stream and output follow x's device even
+    when another device is current (the table is staged per device)."""
+    g = golden("approx__64o7-p1.19209289551e-06")
+    ap = app.Approximator.from_record(g)
+    x = g.x[np.isfinite(g.x)]
+    want = gpu_eval(dev_table(g.name), x)
+    torch.cuda.set_device(0)
+    x1 = torch.from_numpy(x).to("cuda:1")
+    y1 = generate.run(x1, ap)
+    assert y1.device.index == 1 and np.array_equal(y1.cpu().numpy(), want)
+    sec, y1 = generate.run_single(x1, ap)
+    assert sec > 0 and y1.device.index == 1 and np.array_equal(y1.cpu().numpy(), want)
+    i1 = generate.run_index(x1, ap)
+    assert i1.device.index == 1
+    assert torch.cuda.current_device() == 0
+    # a table staged on one device refuses another device's pointers instead of faulting
+    with pytest.raises(ValueError):
+        generate._launch(torch, generate.device_table(ap, 0), x1, torch.empty_like(x1))
+
+
+def test_staged_table_follows_the_tree_content():
+    """The per-call check is the identity of tree_1d; a NEW array with the same content keeps the
+    staged table, a new array with other content re-stages."""
+    g = golden("approx__64o7-p1.19209289551e-06")
+    ap = app.Approximator.from_record(g)
+    x = g.x[np.isfinite(g.x)]
+    y0 = generate.run(x, ap)
+    t0 = generate.device_table(ap)
+    ap.tree_1d = np.array(ap.tree_1d, copy=True)
+    assert generate.device_table(ap) is t0
+    t = np.array(ap.tree_1d, copy=True)
+    t[1] += 1.0                                   # c0 of the root record; the root is not a leaf
+    leaf0 = int(np.nonzero(t[g.max_order + 4::g.max_order + 6] == np.arange(0, len(t), g.max_order + 6))[0][0])
+    t[leaf0 * (g.max_order + 6) + 1] += 1.0       # c0 of the first leaf in storage order
+    ap.tree_1d = t
+    ap.coeff = None
+    ap.interval_a = None
+    assert generate.device_table(ap) is not t0
+    assert not np.array_equal(generate.run(x, ap), y0)
 
 
 def test_integration_stub_pure_ctypes():

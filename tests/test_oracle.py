@@ -13,6 +13,10 @@ NAMES = all_golden_names()
 # oracle-vs-reference: both evaluate in the same operation order; only np.dot's BLAS summation
 # order and numpy's pow differ -> a couple of eps of sum|c_i B_i| (measured max 2.1)
 ORACLE_ULPS = 4
+# tables whose tree_1d is in the standard layout the tree-walking restatements follow; the one
+# trim_data fixture (whose links the reference's own walk cannot follow) is covered through
+# tables.flatten + the numpy oracle below and in tests/test_tables.py
+TREE_NAMES = [n for n in NAMES if not n.startswith("trim__")]
 
 
 def leaf_ordinals(g, offsets):
@@ -24,7 +28,7 @@ def leaf_ordinals(g, offsets):
     return np.array([pos[int(o)] for o in offsets], dtype=np.int32)
 
 
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", TREE_NAMES)
 def test_c_oracle_matches_reference(name):
     g = golden(name)
     y, off, cond = oracle.c_eval_tree(g.tree_1d, g.max_order, g.num_levels, g.basis, g.x)
@@ -62,7 +66,7 @@ def test_literal_walk_equals_searchsorted(name):
     assert np.array_equal(leaf_ordinals(g, offs), oracle_np.leaf_index(b, x))
 
 
-@pytest.mark.parametrize("name", [n for n in NAMES if "cheb" in n or n.startswith("approx")])
+@pytest.mark.parametrize("name", [n for n in TREE_NAMES if "cheb" in n or "approx" in n])
 def test_reference_generated_kernel(name):
     """oracle/_ref: the reference's own gen_cheb text compiled as C (oracle/build_ref.py) agrees
     with the reference's Python evaluator.  Its rescale is (2./(b-a))*(x-a)-1 (generate.py:83),
@@ -89,3 +93,17 @@ def test_reference_error_bound_holds_in_golden():
         dom = (g.x >= g.lower_bound) & (g.x < g.upper_bound) & np.isfinite(g.f_true)
         rel = np.max(np.abs(g.y_ref[dom].astype(np.float64) - g.f_true[dom])) / g.fmax
         assert rel <= g.allowed_error * 1.5 + 8 * np.finfo(g.dtype).eps, (name, rel)
+
+
+def test_parity_matrix_is_complete():
+    """north_star: kernels specialised on basis x order 3..13 x dtype.  Every one of the 66
+    combinations has a table fitted by the reference's own fitter and frozen with the reference's
+    own evaluation (tests/golden/make_golden.py matrix_jobs), so every parametrised parity test
+    (CPU oracle here, CUDA path in test_gpu_parity.py) runs on all of them."""
+    have = set()
+    for name in NAMES:
+        g = golden(name)
+        have.add((g.basis, int(g.max_order), np.dtype(g.dtype).name))
+    want = {(b, o, d) for b in ("chebyshev", "legendre", "monomial") for o in range(3, 14)
+            for d in ("float32", "float64")}
+    assert not (want - have), sorted(want - have)

@@ -31,12 +31,16 @@ def test_plan_is_consistent(name):
     assert info["lower_bound"] == float(f.breaks[0]) and info["upper_bound"] == float(f.breaks[-1])
     assert 1 <= info["grid_cells"] <= (1 << 20)
     assert info["smem_bytes"] <= 227 * 1024
-    assert info["residency"] in (0, 1, 2, 3, 4)
+    assert info["residency"] in (0, 1, 2, 3, 4, 9)
     if info["residency"] == 4:
         assert f.n_leaves == 2 and info["smem_bytes"] == 0
     if info["residency"] in (1, 3):
         assert info["bank_copies"] >= 2 and f.n_leaves > (32 if f.dtype == np.float32 else 16)
-    if info["lookup_mode"] == 2:                       # in-register bitmap rank
+    if info["residency"] == 9:                         # 8 copies of 16-byte padded records, 128-bit gathers
+        assert info["bank_copies"] == 8 and info["header_packed"] == 0 and info["cell_records"] == 0
+        assert info["record_stride"] * f.dtype.itemsize % 16 == 0
+        assert f.n_leaves > (32 if f.dtype == np.float32 else 16)
+    if info["lookup_mode"] in (2, 3):                  # rank from a register bitmap / from rank words
         assert info["search_steps"] == 0
     hdr = 0 if f.basis == "monomial" else {0: 2, 1: 1, 2: 0}[info["header_packed"]]
     assert info["record_stride"] >= f.order + 1 + hdr
@@ -47,21 +51,25 @@ def test_saved_tables_plan():
     for name in SAVED:
         info = plan(name)
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["header_packed"] in (1, 2) and info["image_bytes"] <= 48 * 1024, (name, info)
+        assert info["header_packed"] in (1, 2) or info["residency"] == 9, (name, info)
+        assert info["image_bytes"] <= 48 * 1024, (name, info)
     assert plan("approx__32o6-p1.19209289551e-06")["lookup_mode"] == 2          # BASELINE configs[1]
     assert plan("approx__32o6-p1.19209289551e-06")["residency"] == 0
     assert plan("approx__32o3-p1.19209289551e-06")["residency"] == 1            # 62 leaves > 32 banks
     assert plan("approx__64o13-p1.19209289551e-06")["residency"] == 4           # two leaves: select
     big = plan("approximations__64o5-p2.22044604925e-14")                       # 429 leaves
-    assert big["residency"] == 3 and big["bank_copies"] == 8
+    # full per-bank replication (16 copies) does not fit: 8 copies of 64-byte records, 128-bit loads,
+    # and the leaf from rank words instead of a 1 KB first[] table
+    assert big["residency"] == 9 and big["bank_copies"] == 8 and big["lookup_mode"] == 3
 
 
 def test_config_tables_plan():
     cfg3 = plan("gen__cfg3_j0_cheb_o13_f64")
     assert cfg3["lookup_mode"] == 2 and cfg3["header_packed"] == 2 and cfg3["residency"] == 0   # 8 equal leaves
-    for name, k in (("gen__cfg4_f1_leg_o7_f32", 4), ("gen__cfg4_f1_leg_o7_f64", 6)):
+    for name, k, res in (("gen__cfg4_f1_leg_o7_f32", 4, 1), ("gen__cfg4_f1_leg_o7_f64", 6, 9)):
         info = plan(name)                               # deep skewed trees: grid + bounded search
         assert info["search_steps"] == k and info["lookup_mode"] == 1 and info["header_packed"] == 0
+        assert info["residency"] == res                 # fp32: per-bank copies fit; fp64: 8 x 128-bit
 
 
 def test_smaller_shared_memory_changes_the_residency():
@@ -86,9 +94,12 @@ def test_hooks(monkeypatch):
     info = plan(name)
     assert info["grid_cells"] <= 8 and info["search_steps"] >= 1 and info["lookup_mode"] == 1
     monkeypatch.delenv("AI_B200_MAX_CELLS")
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 9):
         monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
         assert plan(name)["residency"] == mode
+    monkeypatch.delenv("AI_B200_FORCE_MODE")
+    monkeypatch.setenv("AI_B200_NO_VEC_MODE", "1")
+    assert plan("approximations__64o5-p2.22044604925e-14")["residency"] == 3     # the partial-copy layout it replaces
 
 
 def test_large_tables_plan():
@@ -169,3 +180,17 @@ def test_planner_invariants_on_random_tables(kind, dtype):
         if info["search_steps"] > 0:                                 # breakpoints off the grid
             assert info["lookup_mode"] == 1 and info["header_packed"] != 2 and not info["cell_records"]
     assert len(seen) >= 2
+
+
+def test_plan_rejects_a_nonsensical_leaf_count_with_a_status():
+    """No C++ exception may cross the C ABI: n_leaves far beyond any table is AI_ERR_UNSUPPORTED
+    before anything is allocated (the arrays behind the pointers are never read)."""
+    import ctypes
+    from adaptive_interpolation_b200 import _cabi
+    L = _cabi.lib()
+    one = np.zeros(4, dtype=np.float64)
+    info = _cabi.TableInfo()
+    rc = L.ai_table_plan(0, 3, 1, 1 << 40, one.ctypes.data, one.ctypes.data, 0, ctypes.byref(info))
+    assert rc == 4 and b"leaves" in L.ai_last_error()
+    rc = L.ai_table_plan(0, 3, 1, 0, one.ctypes.data, one.ctypes.data, 0, ctypes.byref(info))
+    assert rc == 2

@@ -54,12 +54,30 @@ def test_flatten_detects_soa_mismatch():
         tables.flatten(ap)
 
 
-def test_trim_data_rejected():
-    g = golden("approx__64o7-p1.19209289551e-06")
-    ap = app.Approximator.from_record(g)
-    ap.optimizations = ["trim_data"]
-    with pytest.raises(Exception):
-        tables.flatten(ap)
+def test_trim_data_layout_flattens_to_the_same_leaves():
+    """approximator.py:202-206,232-233: a table built with optimizations=[..., "trim_data"] stores
+    inner nodes as [mid, left node, right node] and leaves as [mid, self, self, c.., a, b].
+    flatten() scans it in preorder; the result equals the SoA arrays the reference stored beside it."""
+    g = golden("trim__j0_cheb_o6_f64")
+    assert "trim_data" in g.optimizations
+    f = tables.flatten(g)
+    assert np.array_equal(f.breaks[:-1], np.asarray(g.interval_a)) and f.breaks[-1] == g.interval_b[-1]
+    assert np.array_equal(f.coef.ravel(), np.asarray(g.coeff))
+    n_inner = f.n_leaves - 1
+    assert len(g.tree_1d) == 3 * n_inner + (g.max_order + 6) * f.n_leaves
+
+
+def test_trim_data_layout_rejects_malformed_trees():
+    g = golden("trim__j0_cheb_o6_f64")
+    t = np.asarray(g.tree_1d).copy()
+    with pytest.raises(ValueError):
+        tables.flatten_tree_1d_trim(t[:-1], g.max_order)             # ends inside a leaf
+    bad = t.copy()
+    bad[1] = 5.0                                                     # root's left child is not node 1
+    with pytest.raises(ValueError):
+        tables.flatten_tree_1d_trim(bad, g.max_order)
+    with pytest.raises(ValueError):
+        tables.flatten_tree_1d_trim(t[3:], g.max_order)              # root removed: not one full tree
 
 
 def test_single_leaf_and_order_one():

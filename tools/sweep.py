@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--tables", default="bench")
     ap.add_argument("--tag", default="sweep")
+    ap.add_argument("--clustered", default="cfg4", choices=["cfg4", "all", "none"],
+                    help="also time points clustered at the breakpoints: for the config-4 tables (default), all, none")
     args = ap.parse_args()
     n = 1 << args.log2n
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -104,19 +106,28 @@ def main():
                "search_steps": info["search_steps"], "image_bytes": info["image_bytes"],
                "blocks_per_sm": info["blocks_per_sm"], "grid_cells": info["grid_cells"],
                "residency": info["residency"], "lookup_mode": info["lookup_mode"], "smem_bytes": info["smem_bytes"]}
-        for order in ("random", "sorted"):
+        orders = ("random", "sorted", "clustered") if (args.clustered == "all" or name.startswith("gen__cfg4")) \
+            and args.clustered != "none" else ("random", "sorted")
+        for order in orders:
             if order == "sorted":
                 x = torch.sort(x)[0]
+            elif order == "clustered":
+                # BASELINE configs[3]'s own input distribution (bench.fill_points, the device port of
+                # tests/golden/make_golden.py:make_points(clustered=True))
+                import bench
+                bench.fill_points(torch, x, f, "clustered", gen)
             med, mn = time_ms(lambda: tab.eval_ptr(x.data_ptr(), y.data_ptr(), n, s), args.reps)
             row[order] = {"ms_median": med, "ms_min": mn, "gpts": n / (med * 1e-3) / 1e9,
                           "gbs": 2.0 * esz * n / (med * 1e-3) / 1e9, "frac_hbm": 2.0 * esz * n / (med * 1e-3) / 1e9 / hbm,
                           "tflops_ref_model": (8 + 4 * f.order) * n / (med * 1e-3) / 1e12}
         out["rows"].append(row)
         r, so = row["random"], row["sorted"]
-        print("%-42s %-9s %3d %-4s %5d %2d %7d | %9.3f %8.1f %6.1f | %9.3f %8.1f %6.1f" % (
+        cl = row.get("clustered")
+        print("%-42s %-9s %3d %-4s %5d %2d %7d | %9.3f %8.1f %6.1f | %9.3f %8.1f %6.1f%s" % (
             name[:42], f.basis, f.order, "f32" if esz == 4 else "f64", f.n_leaves, info["search_steps"],
             info["image_bytes"], r["ms_median"], r["gpts"], 100 * r["frac_hbm"], so["ms_median"], so["gpts"],
-            100 * so["frac_hbm"]))
+            100 * so["frac_hbm"],
+            (" | clustered %9.3f %8.1f %6.1f" % (cl["ms_median"], cl["gpts"], 100 * cl["frac_hbm"])) if cl else ""))
         del x, y, tab
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "%s.json" % args.tag), "w") as fh:
