@@ -18,7 +18,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "_lib")
-OBJDIR = os.path.join(LIBDIR, "obj")
+OBJROOT = os.path.join(ROOT, "build")          # scratch: git-ignored AND gpurun-ignored (objects never travel)
+OBJDIR = os.path.join(OBJROOT, "obj")
 LIB = os.path.join(LIBDIR, "libai_b200.so")
 
 NVCC_FLAGS = [
@@ -64,15 +65,17 @@ def is_current():
         return fh.read().strip() == fingerprint()
 
 
-def build(force=False, verbose=False, defines=(), out=None):
+def build(force=False, verbose=False, defines=(), out=None, only=None):
     """Compile every CUDA translation unit for sm_100a and link the shared library.
-    `defines` / `out` build a tuning variant (tools/tune.py) next to the product library."""
+    `defines` / `out` build a tuning variant (tools/tune.py) next to the product library; `only`
+    (base names of .cu files) recompiles just those units with the defines and links them with the
+    product's objects for the rest (a variant for ONE kernel family in seconds instead of minutes)."""
     variant = out is not None
     lib = os.path.join(LIBDIR, out) if variant else LIB
     if not variant and not force and is_current():
         return LIB
     nvcc = nvcc_path()
-    objdir = os.path.join(LIBDIR, "obj_" + out) if variant else OBJDIR
+    objdir = os.path.join(OBJROOT, "obj_" + out) if variant else OBJDIR
     os.makedirs(objdir, exist_ok=True)
     dflags = ["-D" + d for d in defines]
 
@@ -84,10 +87,20 @@ def build(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         return obj, r.stderr
 
-    workers = max(1, min(len(sources()), os.cpu_count() or 1))
+    todo = sources()
+    reused = []
+    if only is not None:
+        if not variant:
+            raise ValueError("`only` is for variants")
+        todo = [src for src in sources() if os.path.basename(src) in only]
+        reused = [os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o") for src in sources() if src not in todo]
+        missing = [o for o in reused if not os.path.exists(o)]
+        if missing:
+            raise RuntimeError("build the product library first (missing %s)" % missing[0])
+    workers = max(1, min(len(todo), os.cpu_count() or 1))
     with concurrent.futures.ThreadPoolExecutor(workers) as ex:
-        results = list(ex.map(compile_one, sources()))
-    objs = [o for o, _ in results]
+        results = list(ex.map(compile_one, todo))
+    objs = [o for o, _ in results] + reused
     if verbose:
         for _, log in results:
             sys.stderr.write(log)

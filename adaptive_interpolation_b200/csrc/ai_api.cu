@@ -471,9 +471,12 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     const int pad = (gp.K > 0) ? (1 << gp.K) : 0;
     const int off_first = 0;
     int fshift = (L <= 256) ? 2 : (L <= 65536 ? 1 : 0);   // 8-, 16- or 32-bit entries
-    // the leaf as a rank from memory (Lookup::rank16_guess) where a first[] table would be read with
-    // bank conflicts: more than 128 bytes (32 words) of it, leaf-indexed records, no search
-    size_t rank16_min = 128;                             // (tuning hook: AI_B200_RANK16_MIN_BYTES)
+    // the leaf as a rank from memory (Lookup::rank16_guess) where a large first[] table would be read
+    // with bank conflicts: leaf-indexed records, no search
+    // Measured (A/B on one box, random points): against a 1 KB+ first[] table the rank words win
+    // (429-leaf fp64 table 80.0 -> 81.4% of HBM); against the 320-640 byte tables of the fp32 order-3
+    // tables the extra integer work loses (69 leaves: 98.9 -> 93.7%), so those keep first[].
+    size_t rank16_min = 1024;                            // (tuning hook: AI_B200_RANK16_MIN_BYTES)
     if (const char* e = std::getenv("AI_B200_RANK16_MIN_BYTES")) rank16_min = (size_t)std::max(0L, std::atol(e));
     const bool rank16 = !gp.rank16.empty() && !cell_records && gp.K == 0 && !gp.rank_mode
                         && (size_t)gp.G * (size_t)(4 >> fshift) > rank16_min;

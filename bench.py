@@ -67,6 +67,7 @@ CPU_SAMPLE_LOG2 = 26
 CFG3_GLOBAL_LOG2 = 30           # BASELINE configs[2]: 2^30 points sharded over the GPUs
 CFG5_GLOBAL_LOG2 = 30           # BASELINE configs[4]: every saved table at 2^30 points
 SUSTAINED_SECONDS = 2.0
+CONFIG_IDLE_SECONDS = 0.25      # idle gap before each per-config measurement (the power window recovers)
 
 NCU_SUMMARIES = {   # workload -> committed `ncu --set full` summary (tools/ncu_summary.py)
     "cfg2_j0_cheb_o6_f32": "r1_ncu_cfg2_cheb_o6_f32.json",
@@ -454,31 +455,7 @@ def main():
         sl = slice(0, 1 << 14)
         xs_np, ys_np = x[sl].cpu().numpy(), y[sl].cpu().numpy()
         dev_units = None
-
-        # ---- sustained: the same launch back to back for >= 2 s (north_star "sustains")
         sustained = None
-        if not args.no_sustained:
-            batch = 200
-            first = last = None
-            t_begin = time.perf_counter()
-            launches = 0
-            clocks.mark()
-            # the batch count comes from the max-over-ranks step time, so every rank runs the same
-            # number of (barrier-bracketed) batches
-            n_batches = max(2, int(np.ceil(SUSTAINED_SECONDS / (total_ms / args.steps * 1e-3 * batch))))
-            for _ in range(n_batches):
-                _, ms, _ = time_table(tab, x, y, batch, 0, per_launch=False)
-                launches += batch
-                first = ms if first is None else first
-                last = ms
-            sc = clocks.mark()
-            last = sharding.max_over_ranks(last, dgroup, dev)
-            sustained = {"seconds": time.perf_counter() - t_begin, "launches": launches,
-                         "kernel_ms_first_batch": first, "kernel_ms_last_batch": last,
-                         "achieved": 2.0 * esz * n_local / (last * 1e-3) / 1e9,
-                         "frac": frac_of_hbm(n_local, esz, last), "clocks": sc,
-                         "note": "back-to-back launches of the headline kernel in batches of %d, no host sync inside a batch; "
-                                 "frac is the LAST batch (sw_power_cap here is a note, not a rejection)" % batch}
 
         # ---- e2e: host buffers through ai_eval_host_* (pinned), copies inside the timed region
         e2e = None
@@ -556,7 +533,7 @@ def main():
                                                              flat.order, "float" if esz == 4 else "double"),
                     "algorithmic_bytes_per_point": 2 * esz, "points_per_launch": n_local,
                     "kernel_ms_avg": kernel_ms, "kernel_ms_min": kernel_ms_min,
-                    "flops_per_point": 8 + 4 * flat.order, "sustained": sustained}
+                    "flops_per_point": 8 + 4 * flat.order, "sustained": None}
         fma_peak = {}
         try:
             for dt_id, nm in ((0, "f32"), (1, "f64")):
@@ -585,6 +562,8 @@ def main():
                 nl = shard_points(n_glob)
                 xx, yy = arena.views(ff.dtype.type, nl)
                 fill_points(torch, xx, ff, kind, gen, rank, world)
+                torch.cuda.synchronize(dev)
+                time.sleep(CONFIG_IDLE_SECONDS)          # every config is a burst like the headline, not the tail of the previous one
                 clocks.mark()
                 tot, kms, kmin = time_table(tt, xx, yy, steps, cwarm)
                 ck = clocks.mark()
@@ -660,6 +639,8 @@ def main():
                 rec = run_config("cfg5", nm, 1 << CFG5_GLOBAL_LOG2, "uniform", True, steps=5)
                 rows.append({k: rec[k] for k in ("workload", "dtype", "order", "leaves", "residency", "value",
                                                  "kernel_ms", "frac")})
+                rows[-1]["sm_mhz"] = rec["clocks"].get("sm_mhz")
+                rows[-1]["reasons"] = rec["clocks"].get("reasons")
             fr = np.array([r["frac"] for r in rows])
             lo7 = np.array([r["frac"] for r in rows if r["order"] <= 7 and not r["workload"].startswith("large__")])
             configs.append({"config": "cfg5", "workload": "all %d saved tables (approx/, approximations/) + %d refits of "
@@ -670,7 +651,36 @@ def main():
                             "frac_min": float(fr.min()), "frac_median": float(np.median(fr)), "frac_max": float(fr.max()),
                             "frac_min_saved_order_le7": float(lo7.min()) if lo7.size else None,
                             "value_median": float(np.median([r["value"] for r in rows])), "unit": UNIT,
-                            "clocks": clocks.mark(), "tables": rows})
+                            "clocks": {"sm_mhz_min_over_tables": min([r["sm_mhz"] for r in rows if r["sm_mhz"]] or [None]),
+                                       "reasons": sorted({k for r in rows for k in (r["reasons"] or [])}),
+                                       "sm_max_mhz": clocks.max_mhz},
+                            "tables": rows})
+        # ---- sustained: the same launch back to back for >= 2 s (north_star "sustains")
+        if not args.no_sustained:
+            fill_points(torch, x, flat, dist_kind, gen, rank, world)      # the arena was reused by the configs
+            batch = 200
+            first = last = None
+            t_begin = time.perf_counter()
+            launches = 0
+            clocks.mark()
+            # the batch count comes from the max-over-ranks step time, so every rank runs the same
+            # number of (barrier-bracketed) batches
+            n_batches = max(2, int(np.ceil(SUSTAINED_SECONDS / (total_ms / args.steps * 1e-3 * batch))))
+            for _ in range(n_batches):
+                _, ms, _ = time_table(tab, x, y, batch, 0, per_launch=False)
+                launches += batch
+                first = ms if first is None else first
+                last = ms
+            sc = clocks.mark()
+            last = sharding.max_over_ranks(last, dgroup, dev)
+            sustained = {"seconds": time.perf_counter() - t_begin, "launches": launches,
+                         "kernel_ms_first_batch": first, "kernel_ms_last_batch": last,
+                         "achieved": 2.0 * esz * n_local / (last * 1e-3) / 1e9,
+                         "frac": frac_of_hbm(n_local, esz, last), "clocks": sc,
+                         "note": "back-to-back launches of the headline kernel in batches of %d, no host sync inside a batch; "
+                                 "frac is the LAST batch (sw_power_cap here is a note, not a rejection)" % batch}
+
+        roofline["sustained"] = sustained
         all_clocks = clocks.summary()
 
     cpu = None

@@ -266,7 +266,9 @@ def test_saved_tables_take_the_packed_header():
     qualifies; the deep config-4 trees (breakpoints with > 15 significant bits) do not."""
     for name in SAVED:
         info = dev_table(name).info()
-        assert info["header_packed"] in (1, 2), (name, info)
+        # (the 429-leaf table takes the eight-copy layout, whose 16-byte padded records keep [a, s]:
+        # with or without the one-word header its record is four 128-bit loads)
+        assert info["header_packed"] in (1, 2) or info["residency"] == 9, (name, info)
     assert dev_table("gen__cfg3_j0_cheb_o13_f64").info()["header_packed"] == 2       # 8 equal leaves
     assert dev_table("approx__64o7-p2.22044604925e-14").info()["header_packed"] == 2  # 64 equal leaves
     assert dev_table("approx__64o6-p1.19209289551e-06").info()["header_packed"] == 1

@@ -14,7 +14,7 @@ tag=${2:-r2}
 mkdir -p gpurun_out
 case "$stage" in
 tests)
-    python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+    python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${tag}.log 2>&1; tail -5 gpurun_out/pytest_${tag}.log
     for sd in 1 2 3; do AI_TEST_SEED=$sd python -m pytest tests -m gpu -x -q -k lookup_exact_on_random_tables 2>&1 | tail -1; done
     ;;
 bench)
@@ -38,7 +38,7 @@ ncu)
     name=$3; workload=$4; shift 4
     args="--workload $workload --steps 4 --warmup 3 --no-e2e --no-cpu --no-configs --no-sustained $*"
     python bench.py $args > gpurun_out/plain_${name}.log 2>&1 || { tail -5 gpurun_out/plain_${name}.log; exit 1; }
-    ncu --set full --clock-control none --import-source on -k regex:eval_kernel -s 4 -c 1 -f -o /tmp/prof_${name} python bench.py $args > gpurun_out/ncu_${name}.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:eval_ -s 4 -c 1 -f -o /tmp/prof_${name} python bench.py $args > gpurun_out/ncu_${name}.log 2>&1
     ncu -i /tmp/prof_${name}.ncu-rep --page raw --csv > gpurun_out/ncu_${tag}_${name}_raw.csv
     ncu -i /tmp/prof_${name}.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/ncu_${tag}_${name}_source.csv.gz
     ls -la /tmp/prof_${name}.ncu-rep gpurun_out/ncu_${tag}_${name}_*

@@ -14,6 +14,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
+    "bin_t128_b4": ["AI_BIN_THREADS=128", "AI_BIN_MIN_BLOCKS=4"],
+    "bin_t128_b5_np": ["AI_BIN_THREADS=128", "AI_BIN_MIN_BLOCKS=5", "AI_BIN_PREFETCH=0"],
+    "bin_t128_b6_np": ["AI_BIN_THREADS=128", "AI_BIN_MIN_BLOCKS=6", "AI_BIN_PREFETCH=0"],
+    "bin_t256_b3_np": ["AI_BIN_THREADS=256", "AI_BIN_MIN_BLOCKS=3", "AI_BIN_PREFETCH=0"],
+    "bin_t64_b8": ["AI_BIN_THREADS=64", "AI_BIN_MIN_BLOCKS=8", "AI_BIN_Q=13"],
+    "bin_t64_b10_np": ["AI_BIN_THREADS=64", "AI_BIN_MIN_BLOCKS=10", "AI_BIN_PREFETCH=0", "AI_BIN_Q=13"],
+}
+BIN_TABLES = "gen__cfg3_j0_cheb_o13_f64,mx__cheb_o10_f64,mx__cheb_o12_f64,mx__cheb_o13_f64"
+
+VARIANTS = {
     # tag: defines   (defaults: AI_BLOCK=512 AI_UNROLL=6 AI_UNROLL_F64=5 AI_PREFETCH=1 AI_UNIFORM_PATH=2 AI_PACKED_F32=1)
     "debug_bounds": ["AI_DEBUG_BOUNDS=1"],
     "packed_uniform_only": ["AI_PACKED_F32=2"],
