@@ -149,6 +149,7 @@ struct ai_table {
     int cell_records = 0;              // 1: one record per coarse cell (view.rank_mode 2)
     int uniform_hdr = 0;               // 1: records carry no header, computed from the cell (modes kSmemU / kSmemBankU)
     int rank16 = 0;                    // 1: the first[] section holds rank words (view.rank_mode bit 2)
+    int compact = 0;                   // 1: kGlobalC image (headerless 32-byte records per coarse cell)
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
@@ -171,6 +172,10 @@ struct GridPlan {
     int coarse_ok = 0;                   // div_* map a fine cell to its coarse cell, coarse_leaf is valid
     std::vector<uint32_t> coarse_leaf;   // leaf of every coarse cell
     std::vector<uint32_t> rank16;        // Lookup::rank16_guess words (empty: not available)
+    // wide division (kGlobalC, grids of up to 2^20 fine cells): coarse = ((fine - g0) * wide_mul) >> wide_shift (64-bit)
+    int wide_ok = 0;
+    unsigned wide_mul = 0, wide_shift = 0;
+    std::vector<uint32_t> wide_coarse_leaf;
 };
 
 long long gcd_ll(long long a, long long b) {
@@ -195,6 +200,21 @@ void plan_rank(const std::vector<double>& b, GridPlan* gp) {
     if (q == 0) q = G;                                   // single leaf
     const long long Gc = (G + q - 1) / q;
     if (Gc > (1 << 21)) return;
+    // 64-bit product form for large grids: floor(v / q) = (v * M) >> s, checked for every fine cell
+    for (int sft = 0; sft <= 40 && !gp->wide_ok; ++sft) {
+        const unsigned long long M = ((1ull << sft) + (unsigned long long)q - 1) / (unsigned long long)q;
+        if (M == 0 || M >= (1ull << 32)) continue;
+        bool ok = true;
+        for (int v = 0; v < G && ok; ++v)
+            ok = (unsigned)(((unsigned long long)(unsigned)v * M) >> sft) == (unsigned)(v / q);
+        if (ok) { gp->wide_ok = 1; gp->wide_mul = (unsigned)M; gp->wide_shift = (unsigned)sft; }
+    }
+    if (gp->wide_ok) {
+        gp->wide_coarse_leaf.resize((size_t)Gc);
+        for (long long c = 0; c < Gc; ++c) gp->wide_coarse_leaf[(size_t)c] = gp->first[(size_t)(c * q)];
+        for (int g = 0; g < G && gp->wide_ok; ++g)
+            if (gp->wide_coarse_leaf[(size_t)(g / q)] != gp->first[g]) gp->wide_ok = 0;     // a breakpoint off the coarse grid
+    }
     unsigned mul = 0, sh = 0;
     bool found = false;
     for (int S = 31; S >= 0 && !found; --S) {
@@ -264,7 +284,7 @@ bool cells_for(const std::vector<double>& b, int p, long long* g0, long long* gl
     return true;
 }
 
-int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
+int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out, int64_t exact_budget_override = 0) {
     const int64_t L = (int64_t)b.size() - 1;
     const long long rep_limit = (dtype == AI_DTYPE_F32) ? (1LL << 24) : (1LL << 30);
     auto fits = [&](int p, int gmax, long long* g0, long long* gl) {
@@ -290,6 +310,7 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out) {
         budget_exact = (int)std::min<int64_t>(kGridMaxLarge, std::max<int64_t>(kGridMaxExact, 4 * L));
         budget_search = (int)std::min<int64_t>(kGridMaxLarge, 4 * L);
     }
+    if (exact_budget_override > 0) budget_exact = (int)std::min<int64_t>(exact_budget_override, 1 << 22);
     if (p_exact >= 0 && fits(p_exact, grid_budget(budget_exact), &g0, &gl)) {
         p = p_exact;
         exact = true;
@@ -532,6 +553,113 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     return AI_OK;
 }
 
+// The kGlobalC image of a dyadic table too large for shared memory (see ai_kernels.cuh):
+//   [first[] by coarse cell][breaks][4-bit level per coarse cell][records: c0..cn per coarse cell, 32-byte padded]
+// Possible when the EXACT grid exists (every breakpoint on a cell edge), every leaf spans 2^k
+// coarse cells starting at a multiple of 2^k, and the kernel's header arithmetic reproduces the
+// stored [a, 2/(b-a)] of every leaf bit for bit:  a = fma(first cell, w, lb),  2/(b-a) = S1 * 2^-k.
+constexpr int64_t kCompactMaxCells = 1 << 17;       // 64 KB of levels in shared memory
+template <typename T>
+bool build_compact_image(ai_table* t, const GridPlan& gp, std::vector<unsigned char>* image) {
+    const std::vector<uint32_t>& coarse_leaf = gp.wide_coarse_leaf;
+    const int64_t L = t->L, Gc = (int64_t)coarse_leaf.size();
+    const int n = t->order;
+    if (gp.K != 0 || !gp.wide_ok || Gc < L || Gc > kCompactMaxCells) return false;
+    if (Gc * (int64_t)ai::rec_stride_compact(n, (int)sizeof(T)) * (int64_t)sizeof(T) > ((int64_t)1 << 28)) return false;
+    const bool hdr = t->basis != ai::kMono;
+    // coarse cell width: the narrowest leaf is one cell wide
+    std::vector<int64_t> first_cell((size_t)L, -1), n_cells((size_t)L, 0);
+    for (int64_t c = 0; c < Gc; ++c) {
+        const int64_t i = coarse_leaf[(size_t)c];
+        if (i < 0 || i >= L) return false;
+        if (first_cell[(size_t)i] < 0) first_cell[(size_t)i] = c;
+        if (c != first_cell[(size_t)i] + n_cells[(size_t)i]) return false;          // cells of a leaf are contiguous
+        ++n_cells[(size_t)i];
+    }
+    const T lb = (T)t->breaks[0];
+    T w = 0;
+    for (int64_t i = 0; i < L; ++i) {
+        if (n_cells[(size_t)i] == 1) { w = (T)t->breaks[i + 1] - (T)t->breaks[i]; break; }
+    }
+    if (!(w > 0)) return false;
+    const T s1 = (T)2 / w;
+    std::vector<unsigned char> level((size_t)Gc, 0);
+    for (int64_t i = 0; i < L; ++i) {
+        const int64_t m = n_cells[(size_t)i], c0 = first_cell[(size_t)i];
+        if (m < 1 || (m & (m - 1)) || (c0 & (m - 1))) return false;                  // 2^k cells, aligned
+        int k = 0;
+        while ((1LL << k) < m) ++k;
+        if (k > 15) return false;
+        if (hdr) {
+            const T a = (T)t->breaks[i], b = (T)t->breaks[i + 1];
+            const T s = (T)2 / (b - a);
+            if (std::fma((T)(int)c0, w, lb) != a) return false;                      // the device formula, bit for bit
+            if constexpr (sizeof(T) == 4) {
+                uint32_t sb, s1b;
+                std::memcpy(&sb, &s, 4); std::memcpy(&s1b, &s1, 4);
+                if (s1b - ((uint32_t)k << 23) != sb || (sb >> 23) == 0) return false;
+            } else {
+                uint64_t sb, s1b;
+                std::memcpy(&sb, &s, 8); std::memcpy(&s1b, &s1, 8);
+                const uint64_t dev = ((uint64_t)((uint32_t)(s1b >> 32) - ((uint32_t)k << 20)) << 32) | (uint32_t)s1b;
+                if (dev != sb || ((sb >> 52) & 0x7FF) == 0) return false;
+            }
+        }
+        for (int64_t c = c0; c < c0 + m; ++c) level[(size_t)c] = (unsigned char)k;
+    }
+    const int R = ai::rec_stride_compact(n, (int)sizeof(T));
+    const int fshift = (L <= 65536) ? 1 : 0;                     // first[] by coarse cell: 16- or 32-bit
+    const int off_first = 0;
+    const int off_breaks = round_up16((size_t)Gc * (size_t)(4 >> fshift));
+    const int off_aux = off_breaks + round_up16((size_t)(L + 1) * sizeof(T));
+    const int aux_bytes = hdr ? round_up16((size_t)(Gc + 1) / 2) : 0;
+    const size_t off_records = ((size_t)off_aux + (size_t)aux_bytes + 31) & ~(size_t)31;   // 32-byte aligned records
+    const size_t total = off_records + (size_t)Gc * R * sizeof(T);
+    image->assign((total + 15) & ~(size_t)15, 0);
+    if (fshift == 1) {
+        uint16_t* f16 = reinterpret_cast<uint16_t*>(image->data() + off_first);
+        for (int64_t c = 0; c < Gc; ++c) f16[c] = (uint16_t)coarse_leaf[(size_t)c];
+    } else {
+        std::memcpy(image->data() + off_first, coarse_leaf.data(), (size_t)Gc * sizeof(uint32_t));
+    }
+    T* br = reinterpret_cast<T*>(image->data() + off_breaks);
+    for (int64_t k = 0; k <= L; ++k) br[k] = (T)t->breaks[k];
+    if (hdr) {
+        unsigned char* nib = image->data() + off_aux;
+        for (int64_t c = 0; c < Gc; ++c) nib[c >> 1] |= (unsigned char)(level[(size_t)c] << ((c & 1) * 4));
+    }
+    T* rec = reinterpret_cast<T*>(image->data() + off_records);
+    for (int64_t c = 0; c < Gc; ++c) {
+        const int64_t i = coarse_leaf[(size_t)c];
+        for (int j = 0; j <= n; ++j) rec[c * R + j] = (T)t->coef[(size_t)i * (n + 1) + j];
+    }
+    t->rstride = R;
+    t->packed = 0; t->uniform_hdr = 0; t->rank16 = 0;
+    t->cell_records = 1;
+    t->compact = 1;
+    t->view.first_shift = fshift;
+    t->view.u_w = (double)w; t->view.u_lb = (double)lb; t->view.u_s = (double)s1;
+    if constexpr (sizeof(T) == 4) {
+        uint32_t s1b; std::memcpy(&s1b, &s1, 4);
+        t->view.s0_hi = s1b; t->view.s0_lo = 0;
+    } else {
+        uint64_t s1b; std::memcpy(&s1b, &s1, 8);
+        t->view.s0_hi = (uint32_t)(s1b >> 32); t->view.s0_lo = (uint32_t)s1b;
+    }
+    t->view.image_bytes = (int)image->size();
+    t->view.n_records_elems = (int)(Gc * R);
+    t->view.n_records = (int)Gc;
+    t->view.n_breaks_elems = (int)(L + 1);
+    t->view.off_first = off_first;
+    t->view.off_breaks = off_breaks;
+    t->view.off_records = (int)off_records;
+    t->view.off_aux = off_aux;
+    t->view.aux_bytes = aux_bytes;
+    t->view.wide_mul = gp.wide_mul;
+    t->view.wide_shift = gp.wide_shift;
+    return true;
+}
+
 int prepare_dispatch(int basis, int dtype, int order, int mode, int smem, int* bps) {
     cudaError_t e = cudaErrorInvalidValue;
     if (dtype == AI_DTYPE_F32) {
@@ -599,7 +727,26 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
                                     : build_image<double>(t, gp, false, &image, &hp64, false, &uni);
     if (rc) return rc;
     const bool leaf_image_fits = (size_t)t->view.image_bytes <= smem_cap;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // Too large for shared memory: the compact cell-record image when the table is dyadic (exact grid
+    // allowed to grow to 2^20 cells for this purpose only).
+    bool compact = false;
+    if (((!leaf_image_fits && forced < 0 && !std::getenv("AI_B200_NO_COMPACT")) || forced == ai::kGlobalC)
+        && !std::getenv("AI_B200_NO_CELL_RECORDS")) {
+        GridPlan gpx;
+        if (plan_grid(t->breaks, t->dtype, &gpx, kGridMaxLarge) == AI_OK) {
+            compact = (t->dtype == AI_DTYPE_F32) ? build_compact_image<float>(t, gpx, &image)
+                                                 : build_compact_image<double>(t, gpx, &image);
+            if (compact) {
+                gp = gpx;
+                t->G = gp.G; t->p = gp.p; t->K = gp.K; t->g0 = gp.g0;
+                mode = ai::kGlobalC;
+            }
+        }
+        if (!compact) {       // (build_image state of the leaf layout is rebuilt by the attempts below)
+            t->compact = 0;
+        }
+    }
+    for (int attempt = 0; attempt < 2 && !compact; ++attempt) {
     const bool want_cell = (attempt == 0);
     rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, false, &image, &hp32, want_cell, &uni)
                                     : build_image<double>(t, gp, false, &image, &hp64, want_cell, &uni);
@@ -676,7 +823,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     }
     // two leaves: both records ride in the kernel parameters, element-wise select instead of a gather
     // (the image stays: the reduction and multi-table kernels read it)
-    if (!go_global && ((L == 2 && forced < 0) || (L <= 2 && forced == ai::kSelect))) {
+    if (!compact && !go_global && ((L == 2 && forced < 0) || (L <= 2 && forced == ai::kSelect))) {
         mode = ai::kSelect; copies = 1;
         const int hdr = (t->basis == ai::kMono) ? 0 : 2;
         t->select.assign(1 + 2 * ai::kMaxRecord, 0.0);
@@ -704,8 +851,9 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->copies = copies;
     t->view.copies = copies;
     t->view.bcopies = bcopies;
-    t->smem_resident = (mode != ai::kGlobal);
+    t->smem_resident = (mode != ai::kGlobal && mode != ai::kGlobalC);
     t->eval_smem = 0;
+    if (mode == ai::kGlobalC) t->eval_smem = t->view.aux_bytes;
     if (mode == ai::kSmem || mode == ai::kSmemP || mode == ai::kSmemU) t->eval_smem = t->view.image_bytes;
     if (mode == ai::kSmemV) {
         t->view.soff_breaks = t->view.off_breaks;
@@ -714,12 +862,12 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     } else if (ai::mode_bank(mode)) {
         t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
     }
-    t->aux_smem = (mode == ai::kGlobal) ? 0 : t->view.image_bytes;
+    t->aux_smem = (mode == ai::kGlobal) ? 0 : (mode == ai::kGlobalC ? t->view.aux_bytes : t->view.image_bytes);
     t->view.image = nullptr;
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
-    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0) | (t->rank16 ? 4 : 0);
+    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0) | (t->rank16 ? 4 : 0) | (compact ? 8 : 0);
     t->view.div_mul = gp.div_mul;
     t->view.div_shift = gp.div_shift;
     t->view.div_add = gp.div_add;
@@ -756,7 +904,7 @@ int finish_table(ai_table* t) {
     rc = prepare_dispatch(t->basis, t->dtype, t->order, t->mode, t->eval_smem, &bps);
     if (rc) return rc;
     if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->eval_smem);
-    if (t->mode != ai::kGlobal && t->mode != ai::kSmemV && t->aux_smem > 48 * 1024) {
+    if (t->mode != ai::kGlobal && t->mode != ai::kSmemV && t->mode != ai::kGlobalC && t->aux_smem > 48 * 1024) {
         int dummy = 0;      // opt the reduction kernel (packed layout) into large shared memory too
         rc = prepare_dispatch(t->basis, t->dtype, t->order,
                               t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem), t->aux_smem, &dummy);
@@ -939,7 +1087,7 @@ int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* st
     if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
     const long long want = (n + ai::kBlock - 1) / ai::kBlock;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * 2));
-    if (t->mode == ai::kGlobal) {
+    if (t->mode == ai::kGlobal || t->mode == ai::kGlobalC) {
         ai::index_kernel<T, ai::kGlobal><<<grid, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
     } else {
         if (t->aux_smem > 48 * 1024) {
@@ -977,7 +1125,8 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     const bool from_global = t->mode == ai::kGlobal || t->mode == ai::kSmemV;
     if (from_global) cfg.smem_bytes = 0;
     const int m = from_global ? ai::kGlobal
-                              : (t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem));
+                              : (t->mode == ai::kGlobalC ? ai::kGlobalC
+                                 : (t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem)));
     if constexpr (sizeof(T) == 4) {
         if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, m, cfg, t->view, x, result, n);
         else if (t->basis == ai::kLeg) e = ai::launch_sum_leg_f32(t->order, m, cfg, t->view, x, result, n);

@@ -62,7 +62,7 @@ struct Unit {
     static cudaError_t prepare(int smem_bytes, int* blocks_per_sm) {
         cudaError_t e = raise_smem_limit(eval_kernel<BASIS, ORDER, T, MODE>, smem_bytes);
         if (e != cudaSuccess) return e;
-        if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kSmemU || MODE == kGlobal) {
+        if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kSmemU || MODE == kGlobal || MODE == kGlobalC) {
             e = raise_smem_limit(eval_sum_kernel<BASIS, ORDER, T, MODE>, smem_bytes);
             if (e != cudaSuccess) return e;
         }
@@ -82,6 +82,7 @@ struct Switch {
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::eval(a...);
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::eval(a...);
             if (mode == kSmemV) return Unit<BASIS, T, ORDER, kSmemV>::eval(a...);
+            if (mode == kGlobalC) return Unit<BASIS, T, ORDER, kGlobalC>::eval(a...);
             if constexpr (BASIS != kMono) {          // the monomial record has no header to pack
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::eval(a...);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::eval(a...);
@@ -98,6 +99,7 @@ struct Switch {
     template <typename... A> static cudaError_t sum(int order, int mode, A&&... a) {
         if (order == ORDER) {
             if (mode == kGlobal) return Unit<BASIS, T, ORDER, kGlobal>::sum(a...);
+            if (mode == kGlobalC) return Unit<BASIS, T, ORDER, kGlobalC>::sum(a...);
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::sum(a...);
                 if (mode == kSmemU) return Unit<BASIS, T, ORDER, kSmemU>::sum(a...);
@@ -126,6 +128,7 @@ struct Switch {
             if (mode == kSmemBankN) return Unit<BASIS, T, ORDER, kSmemBankN>::prepare(smem_bytes, bps);
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::prepare(smem_bytes, bps);
             if (mode == kSmemV) return Unit<BASIS, T, ORDER, kSmemV>::prepare(smem_bytes, bps);
+            if (mode == kGlobalC) return Unit<BASIS, T, ORDER, kGlobalC>::prepare(smem_bytes, bps);
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::prepare(smem_bytes, bps);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::prepare(smem_bytes, bps);

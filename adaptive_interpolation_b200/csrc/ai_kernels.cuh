@@ -94,8 +94,17 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              the gather conflict-free with a quarter (fp32) / half (fp64) of the memory the
 //              per-bank layouts need.  Breakpoints (read by the search, if any) are replicated
 //              per bank when they fit beside the records.
+//   kGlobalC   dyadic tables too large for shared memory (the reference's order-3 / 2.2e-14 fits: 10^4
+//              leaves): a random point costs one L1 tag lookup per cache line per load instruction,
+//              so what counts is how many load instructions touch the table per point.  Records are
+//              stored once per COARSE CELL with NO header, padded to 32 bytes, and fetched with
+//              256-bit loads (LDG.E.256: an order-3 fp64 record is ONE instruction and one sector);
+//              the header is computed: a 4-bit level k per cell, staged in shared memory, gives the
+//              leaf's first cell (cell with its low k bits cleared), a = fma(first cell, w, lb) and
+//              2/(b-a) = S1 * 2^-k -- all verified bit for bit on the host.  No grid table, no
+//              breakpoints and no header words are read: one global access per point instead of 5-6.
 enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4, kSmemP = 5, kSmemBankP = 6,
-             kSmemU = 7, kSmemBankU = 8, kSmemV = 9 };
+             kSmemU = 7, kSmemBankU = 8, kSmemV = 9, kGlobalC = 10 };
 constexpr int kVecCopies = 8;
 __host__ __device__ constexpr bool mode_packed_hdr(int mode) { return mode == kSmemP || mode == kSmemBankP; }
 __host__ __device__ constexpr bool mode_uniform_hdr(int mode) { return mode == kSmemU || mode == kSmemBankU; }
@@ -135,6 +144,7 @@ struct TableView {
                                    // bit 1: rec[] holds one record per COARSE CELL (n_records of them);
                                    // bit 2: leaf = rank from one 32-bit word per 16 coarse cells
                                    //        (prefix count << 16 | continuation bits), see Lookup::rank16_guess
+                                   // bit 3: first[] is indexed by the COARSE cell (kGlobalC tables)
     int n_records;                 // records in rec[]: L, or the coarse cell count in rank_mode 2
     unsigned div_mul, div_shift;   // coarse cell = (fine cell * div_mul) >> div_shift  (exact / q)
     unsigned div_add;              // -g0 * div_mul (mod 2^32): folds the "- g0" into the multiply
@@ -144,6 +154,9 @@ struct TableView {
     double inv_order;              // T(1./n) widened: the Legendre-like recurrence's divisor
     unsigned s0_hi, s0_lo;         // packed header: bits of S0 = max_i 2/(b_i-a_i) (fp32: s0_hi only)
     double u_w, u_lb, u_s;         // computed header (kSmemU / kSmemBankU): a_c = fma(c, u_w, u_lb), 2/(b-a) = u_s
+                                   // (kGlobalC: u_w = coarse cell width, s0_hi / s0_lo = bits of S1 = 2 / u_w)
+    int off_aux, aux_bytes;        // kGlobalC: 4-bit level per coarse cell (two per byte), staged in shared memory
+    unsigned wide_mul, wide_shift; // kGlobalC: coarse cell = ((fine cell - g0) * wide_mul) >> wide_shift, 64-bit product
 };
 
 // ---------------------------------------------------------------------------------- helpers
@@ -162,11 +175,17 @@ __host__ __device__ constexpr int rec_stride_global(int basis, int order, int el
     const int per = 16 / elem_bytes;
     return (order + 1 + (basis == kMono ? 0 : 2) + per - 1) / per * per;
 }
+// kGlobalC: [c0..cn] padded to 32 bytes
+__host__ __device__ constexpr int rec_stride_compact(int order, int elem_bytes) {
+    const int per = 32 / elem_bytes;
+    return (order + 1 + per - 1) / per * per;
+}
 // packed header (kSmemP / kSmemBankP): [a|j, c0..cn]
 __host__ __device__ constexpr int rec_stride_packed(int order) { return ((order + 2) | 1); }
 template <int BASIS, int ORDER, typename T, int MODE>
 __host__ __device__ constexpr int rec_stride_for() {
-    return (MODE == kGlobal || MODE == kSmemV) ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
+    return MODE == kGlobalC ? rec_stride_compact(ORDER, (int)sizeof(T))
+           : (MODE == kGlobal || MODE == kSmemV) ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
                            : (mode_packed_hdr(MODE) ? rec_stride_packed(ORDER)
                                                     : (mode_uniform_hdr(MODE) ? rec_stride(kMono, ORDER) : rec_stride(BASIS, ORDER)));
 }
@@ -194,6 +213,7 @@ template <typename T> struct Lookup {
     int nbreaks;                   // elements in breaks[] incl. +inf padding (bounds checks)
     int fshift, rank_mode;
     unsigned div_mul, div_shift, div_add, cont;
+    unsigned wide_mul, wide_shift;
     const unsigned char* first;    // packed 8-bit (L <= 256) or 16-bit entries
     const unsigned char* bbase;    // breaks[] base (uniform); element j of this lane lives at
     int bunit_log2;                //   bbase + (j << bunit_log2) + blane
@@ -204,6 +224,7 @@ template <typename T> struct Lookup {
         g0 = tv.g0; ghi = (int)tv.hi; kstep = tv.kstep; lmax = tv.n_leaves - 1;
         fshift = tv.first_shift; rank_mode = tv.rank_mode; nbreaks = tv.n_breaks_elems;
         div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
+        wide_mul = tv.wide_mul; wide_shift = tv.wide_shift;
         first = base + tv.off_first;
         bbase = base + tv.off_breaks;
         bunit_log2 = (sizeof(T) == 4) ? 2 : 3;
@@ -242,6 +263,10 @@ template <typename T> struct Lookup {
     // the host for every fine cell); the leaf is the number of leaf starts at or before it.
     __device__ __forceinline__ unsigned coarse_cell(T x) const {
         return (cell_abs(x) * div_mul + div_add) >> div_shift;
+    }
+    // kGlobalC tables (grids of up to 2^20 fine cells): the same exact division with a 64-bit product
+    __device__ __forceinline__ unsigned coarse_cell_wide(T x) const {
+        return (unsigned)(((unsigned long long)(cell_abs(x) - (unsigned)g0) * wide_mul) >> wide_shift);
     }
     __device__ __forceinline__ int rank_guess(T x) const {
         const unsigned c = coarse_cell(x);
@@ -289,6 +314,16 @@ template <typename T> struct Lookup {
         if (rank_mode & 4) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = rank16_guess(x[e]);
+            return;
+        }
+        if (rank_mode & 8) {                                     // first[] by coarse cell
+            if (fshift == 1) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) i[e] = (int)reinterpret_cast<const unsigned short*>(first)[coarse_cell_wide(x[e])];
+            } else {
+#pragma unroll
+                for (int e = 0; e < N; ++e) i[e] = (int)reinterpret_cast<const unsigned int*>(first)[coarse_cell_wide(x[e])];
+            }
             return;
         }
         if (fshift == 2) {
@@ -412,6 +447,36 @@ template <int BASIS, int ORDER, typename T> struct Record {
         }
 #pragma unroll
         for (int k = 0; k < N; ++k) v[k] = buf[k];
+    }
+    // kGlobalC: [c0..cn] in global memory, 32-byte aligned: 256-bit read-only loads (LDG.E.256).
+    // Header from the coarse cell: level k -> first cell of the leaf -> a; 2/(b-a) = S1 * 2^-k.
+    __device__ __forceinline__ void load_compact(const T* __restrict__ rec, unsigned cell, unsigned k, T w, T lb,
+                                                 unsigned s1_hi, unsigned s1_lo) {
+        constexpr int C = ORDER + 1;
+        constexpr int PER = 32 / (int)sizeof(T);
+        constexpr int NV = (C + PER - 1) / PER;
+        T buf[NV * PER];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            if constexpr (sizeof(T) == 8) {
+                asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                             : "=d"(buf[4 * q]), "=d"(buf[4 * q + 1]), "=d"(buf[4 * q + 2]), "=d"(buf[4 * q + 3])
+                             : "l"(rec + 4 * q));
+            } else {
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(buf[8 * q]), "=f"(buf[8 * q + 1]), "=f"(buf[8 * q + 2]), "=f"(buf[8 * q + 3]),
+                               "=f"(buf[8 * q + 4]), "=f"(buf[8 * q + 5]), "=f"(buf[8 * q + 6]), "=f"(buf[8 * q + 7])
+                             : "l"(rec + 8 * q));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < C; ++j) v[HDR + j] = buf[j];
+        if constexpr (HDR == 2) {
+            const unsigned first_cell = cell & (0xffffffffu << k);
+            v[0] = fma_((T)(int)first_cell, w, lb);
+            if constexpr (sizeof(T) == 4) v[1] = __uint_as_float(s1_hi - (k << 23));
+            else v[1] = __hiloint2double((int)(s1_hi - (k << 20)), (int)s1_lo);
+        }
     }
     // 16-byte aligned record in global memory: 128-bit read-only loads
     __device__ __forceinline__ void load_vec(const T* __restrict__ rec) {
@@ -598,6 +663,13 @@ template <typename T, int MODE>
 __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
     if constexpr (MODE == kGlobal || MODE == kSelect) {
         return tv.image;
+    } else if constexpr (MODE == kGlobalC) {
+        // only the 4-bit levels are staged; grid table and records stay in global memory
+        const int4* src = reinterpret_cast<const int4*>(tv.image + tv.off_aux);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int k = threadIdx.x; k < tv.aux_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+        __syncthreads();
+        return tv.image;
     } else if constexpr (MODE == kSmem || MODE == kSmemP || MODE == kSmemU) {
         const int4* src = reinterpret_cast<const int4*>(tv.image);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -666,6 +738,11 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
         } else {
             const T* p = records + leaf * R;
             if constexpr (VEC) r.load_vec(p);
+            else if constexpr (MODE == kGlobalC) {
+                unsigned k = 0;
+                if constexpr (Record<BASIS, ORDER, T>::HDR == 2) k = (smem[leaf >> 1] >> ((leaf & 1) * 4)) & 15u;
+                r.load_compact(p, (unsigned)leaf, k, (T)tv.u_w, (T)tv.u_lb, tv.s0_hi, tv.s0_lo);
+            }
             else if constexpr (MODE == kSmemV) r.load_vec_smem(p);
             else if constexpr (PK) r.template load_packed<Copies<T, MODE>::value>(p, tv.s0_hi, tv.s0_lo);
             else if constexpr (mode_uniform_hdr(MODE))
@@ -690,6 +767,9 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
         if constexpr (MODE == kSelect) {
 #pragma unroll
             for (int e = 0; e < (int)(sizeof(li) / sizeof(li[0])); ++e) li[e] = !(xs[e] < sel.mid) ? 1 : 0;
+        } else if constexpr (MODE == kGlobalC) {                   // one record per coarse cell, wide division
+#pragma unroll
+            for (int e = 0; e < (int)(sizeof(li) / sizeof(li[0])); ++e) li[e] = (int)lk.coarse_cell_wide(xs[e]);
         } else {
             lk.leaves(xs, li);
         }
@@ -697,6 +777,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     auto f = [&](T xv) -> T {
         Record<BASIS, ORDER, T> r;
         if constexpr (MODE == kSelect) load_record(r, !(xv < sel.mid) ? 1 : 0);
+        else if constexpr (MODE == kGlobalC) load_record(r, (int)lk.coarse_cell_wide(xv));
         else load_record(r, lk.leaf(xv));
         return eval_record<BASIS, ORDER, T>(r, xv, inv_order);
     };
@@ -1009,7 +1090,7 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
-    static_assert(MODE == kSmem || MODE == kSmemP || MODE == kSmemU || MODE == kGlobal,
+    static_assert(MODE == kSmem || MODE == kSmemP || MODE == kSmemU || MODE == kGlobal || MODE == kGlobalC,
                   "the reduction variant uses the packed layouts only");
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned char* base = table_base<T, MODE>(tv, smem);
@@ -1024,10 +1105,18 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
     const long long gstride = (long long)gridDim.x * kBlock;
     for (long long k = gtid; k < n; k += gstride) {
         const T xv = __ldcs(x + k);
-        const int i = lk.leaf(xv);
+        int i;
+        if constexpr (MODE == kGlobalC) i = (int)lk.coarse_cell_wide(xv);
+        else i = lk.leaf(xv);
         if constexpr (mode_uniform_hdr(MODE)) {
             Record<BASIS, ORDER, T> r;
             r.template load_uniform<1>(records + i * R, i, (T)tv.u_w, (T)tv.u_lb, (T)tv.u_s);
+            acc += (double)eval_record<BASIS, ORDER, T>(r, xv, inv_order);
+        } else if constexpr (MODE == kGlobalC) {
+            Record<BASIS, ORDER, T> r;
+            unsigned k = 0;
+            if constexpr (Record<BASIS, ORDER, T>::HDR == 2) k = (smem[i >> 1] >> ((i & 1) * 4)) & 15u;
+            r.load_compact(records + i * R, (unsigned)i, k, (T)tv.u_w, (T)tv.u_lb, tv.s0_hi, tv.s0_lo);
             acc += (double)eval_record<BASIS, ORDER, T>(r, xv, inv_order);
         } else {
             acc += (double)eval_leaf<BASIS, ORDER, T, 1, false, PK>(records + i * R, xv, inv_order, tv.s0_hi, tv.s0_lo);

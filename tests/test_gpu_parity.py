@@ -162,7 +162,7 @@ def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 9])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 9, 10])
 def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
     """Packed shared memory / bank-private shared memory (full or partial replication) / eight
     128-bit copies / global (L2-resident) / two-leaf select from the kernel parameters: same leaf,
@@ -173,9 +173,11 @@ def test_every_residency_mode_gives_identical_bits(name, mode, monkeypatch):
     monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
     tab = dev_table(name)
     info = tab.info()
-    if tab0.info()["residency"] == 2 and mode != 2:
-        assert info["residency"] == 2
+    if tab0.info()["residency"] in (2, 10) and mode not in (2, 10):
+        assert info["residency"] in (2, 10)
         pytest.skip("table larger than shared memory: L2-resident whatever is asked for")
+    if mode == 10 and info["residency"] != 10:
+        pytest.skip("not a dyadic table: no compact cell-record layout")
     if mode == 4 and info["n_leaves"] > 2:
         assert info["residency"] != 4
         pytest.skip("select mode serves tables with at most two leaves")
@@ -406,7 +408,7 @@ def test_residency_selection():
     assert res["gen__cfg4_f1_leg_o7_f64"]["residency"] == 9                   # too big for 16 copies: 8 x 128-bit
     for name, info in res.items():
         if name.startswith("large__"):
-            assert info["residency"] == 2 and info["n_leaves"] > 4096, (name, info)   # L2-resident
+            assert info["residency"] == 10 and info["n_leaves"] > 4096, (name, info)  # L2-resident, compact cell records
     for name, info in res.items():
         assert info["smem_bytes"] <= 227 * 1024
 

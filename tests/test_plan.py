@@ -31,7 +31,10 @@ def test_plan_is_consistent(name):
     assert info["lower_bound"] == float(f.breaks[0]) and info["upper_bound"] == float(f.breaks[-1])
     assert 1 <= info["grid_cells"] <= (1 << 20)
     assert info["smem_bytes"] <= 227 * 1024
-    assert info["residency"] in (0, 1, 2, 3, 4, 9)
+    assert info["residency"] in (0, 1, 2, 3, 4, 9, 10)
+    if info["residency"] == 10:                        # compact L2-resident layout: headerless 32-byte cell records
+        assert info["cell_records"] == 1 and info["search_steps"] == 0 and info["smem_resident"] == 0
+        assert info["record_stride"] * f.dtype.itemsize % 32 == 0 and info["smem_bytes"] <= 64 * 1024
     if info["residency"] == 4:
         assert f.n_leaves == 2 and info["smem_bytes"] == 0
     if info["residency"] in (1, 3):
@@ -42,7 +45,7 @@ def test_plan_is_consistent(name):
         assert f.n_leaves > (32 if f.dtype == np.float32 else 16)
     if info["lookup_mode"] in (2, 3):                  # rank from a register bitmap / from rank words
         assert info["search_steps"] == 0
-    hdr = 0 if f.basis == "monomial" else {0: 2, 1: 1, 2: 0}[info["header_packed"]]
+    hdr = 0 if (f.basis == "monomial" or info["residency"] == 10) else {0: 2, 1: 1, 2: 0}[info["header_packed"]]
     assert info["record_stride"] >= f.order + 1 + hdr
 
 
@@ -72,10 +75,12 @@ def test_config_tables_plan():
         assert info["residency"] == res                 # fp32: per-bank copies fit; fp64: 8 x 128-bit
 
 
-def test_smaller_shared_memory_changes_the_residency():
+def test_smaller_shared_memory_changes_the_residency(monkeypatch):
     name = "approximations__64o5-p2.22044604925e-14"
     assert plan(name, smem_cap_bytes=160 * 1024)["bank_copies"] == 4
-    assert plan(name, smem_cap_bytes=20 * 1024)["residency"] == 2               # does not fit: L2-resident
+    assert plan(name, smem_cap_bytes=20 * 1024)["residency"] == 10              # does not fit: L2-resident, compact (dyadic)
+    monkeypatch.setenv("AI_B200_NO_COMPACT", "1")
+    assert plan(name, smem_cap_bytes=20 * 1024)["residency"] == 2               # ... or grid table + padded records
     assert plan(name, smem_cap_bytes=20 * 1024)["header_packed"] == 0           # global layout keeps [a, s]
 
 
@@ -94,7 +99,7 @@ def test_hooks(monkeypatch):
     info = plan(name)
     assert info["grid_cells"] <= 8 and info["search_steps"] >= 1 and info["lookup_mode"] == 1
     monkeypatch.delenv("AI_B200_MAX_CELLS")
-    for mode in (0, 1, 2, 9):
+    for mode in (0, 1, 2, 9, 10):
         monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
         assert plan(name)["residency"] == mode
     monkeypatch.delenv("AI_B200_FORCE_MODE")
@@ -108,7 +113,8 @@ def test_large_tables_plan():
         br = np.linspace(0.0, 16.0, n_leaves + 1)
         f = tables.FlatTable("chebyshev", 3, np.float64, br, np.zeros((n_leaves, 4)))
         info = tables.plan(f)
-        assert info["residency"] == 2 and info["smem_resident"] == 0
+        # 131072 equal leaves on [0, 16] are dyadic: compact cell records; 100000 are not: grid + search
+        assert info["residency"] == (10 if k0 else 2) and info["smem_resident"] == 0
         assert (info["search_steps"] == 0) == k0 and info["search_steps"] <= 2
         assert info["grid_cells"] >= n_leaves
 
@@ -194,3 +200,19 @@ def test_plan_rejects_a_nonsensical_leaf_count_with_a_status():
     assert rc == 4 and b"leaves" in L.ai_last_error()
     rc = L.ai_table_plan(0, 3, 1, 0, one.ctypes.data, one.ctypes.data, 0, ctypes.byref(info))
     assert rc == 2
+
+
+def test_refitted_large_tables_take_the_compact_layout(monkeypatch):
+    """The reference's missing order-3 / 2.2e-14 and 2.2e-15 fits (6872-11680 leaves, refitted by its
+    own fitter) are dyadic: exact grid of up to 2^20 fine cells, one headerless 32-byte record per
+    coarse cell, 4-bit levels in shared memory.  With the layout disabled they fall back to grid +
+    search over 16-byte padded records."""
+    for name in NAMES:
+        if not name.startswith("large__"):
+            continue
+        info = plan(name)
+        assert info["residency"] == 10 and info["record_stride"] == 4 and info["search_steps"] == 0, (name, info)
+        assert info["n_leaves"] > 4096
+    monkeypatch.setenv("AI_B200_NO_COMPACT", "1")
+    info = plan("large__approx__64o3-p2.22044604925e-14")
+    assert info["residency"] == 2 and info["record_stride"] == 6

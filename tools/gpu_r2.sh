@@ -34,6 +34,12 @@ ab)
     AI_B200_RANK16_MIN_BYTES=1000000 python tools/sweep.py --tables $T --tag ab_rank16_off_${tag} > gpurun_out/ab_rank16_off_${tag}.txt 2>&1
     tail -8 gpurun_out/ab_*_${tag}.txt
     ;;
+compact)
+    T=large__approx__64o3-p2.22044604925e-14,large__approx__64o3-p2.22044604925e-15,large__approximations__64o3-p2.22044604925e-14,synth:16384:3:f64,synth:131072:3:f64,synth:16384:7:f64,synth:16384:3:f32
+    python tools/sweep.py --tables $T --tag compact_on_${tag} > gpurun_out/compact_on_${tag}.txt 2>&1
+    AI_B200_NO_COMPACT=1 python tools/sweep.py --tables $T --tag compact_off_${tag} > gpurun_out/compact_off_${tag}.txt 2>&1
+    grep -v "^copy\|^table" gpurun_out/compact_on_${tag}.txt gpurun_out/compact_off_${tag}.txt
+    ;;
 ncu)
     name=$3; workload=$4; shift 4
     args="--workload $workload --steps 4 --warmup 3 --no-e2e --no-cpu --no-configs --no-sustained $*"
