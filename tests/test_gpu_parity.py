@@ -297,11 +297,14 @@ def _synthetic_table(n_leaves, lo, hi, order, dtype, seed):
     (131072, 0.0, 16.0, np.float64, True),      # > 65536 leaves: 32-bit grid entries, exact 131072-cell grid in L2
     (100000, 0.0, 16.0, np.float64, False),     # the size of the reference's missing order-3 / 2.2e-15 fits
 ])
-def test_large_table_takes_the_global_path(n_leaves, lo, hi, dtype, expect_k0):
+def test_large_table_is_l2_resident(n_leaves, lo, hi, dtype, expect_k0):
     f = _synthetic_table(n_leaves, lo, hi, 3, dtype, 0)
     tab = tables.DeviceTable(f, 0)
     info = tab.info()
-    assert info["residency"] == 2 and info["smem_resident"] == 0 and info["smem_bytes"] == 0
+    # dyadic tables take the compact cell-record layout (4-bit levels in shared memory), the others
+    # grid table + bounded search over 16-byte padded records; both read their records through L2
+    assert info["residency"] == (10 if expect_k0 else 2) and info["smem_resident"] == 0
+    assert info["smem_bytes"] == (((n_leaves + 1) // 2 + 15) // 16 * 16 if expect_k0 else 0)
     assert (info["search_steps"] == 0) == expect_k0
     rng = np.random.default_rng(11)
     inf = dtype(np.inf)
