@@ -45,6 +45,18 @@ namespace ai {
 #ifndef AI_BLOCK
 #define AI_BLOCK 512               // threads per CTA
 #endif
+// kSelect (two-leaf tables): how many of the LAST record words come from shared memory (128-bit
+// loads) instead of a register select (0: none).  Measured on the saved order-13 tables (random
+// points, % of HBM): fp64 0 / 6 / 10 / 16 words -> 83.5 / 87.4 / 86.0 / 59.7 (a select of a double
+// is two instructions, a 128-bit load of two doubles is one); fp32 0 / 8 / 12 / 16 -> 74.6 / 72.2 /
+// 71.6 / 58.9 (the packed FFMA2 operands are register PAIRS over two points: a vector load of one
+// point's words needs moves to interleave them, a select writes the pair's half directly).
+#ifndef AI_SEL_LDS_F32
+#define AI_SEL_LDS_F32 0
+#endif
+#ifndef AI_SEL_LDS_F64
+#define AI_SEL_LDS_F64 6
+#endif
 #ifndef AI_UNROLL_F64
 #define AI_UNROLL_F64 5            // unroll for the double kernels (2 points per vector: 10 points)
 #endif
@@ -730,11 +742,49 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     if constexpr (kBank) lk.use_replicated_breaks(tv, base);
     const T inv_order = (T)tv.inv_order;
 
+    // kSelect: the LAST words of both records also sit in shared memory, 16-byte aligned, and are
+    // fetched with 128-bit loads (one instruction per 4 floats / 2 doubles, where a select costs one
+    // per word -- two per double): these kernels are bound by ISSUE slots, not by a pipe.  The two
+    // records are 5 sixteen-byte chunks apart, so a quarter-warp's loads hit different bank groups.
+    constexpr int kSelPer = 16 / (int)sizeof(T);
+    constexpr int kSelN = Record<BASIS, ORDER, T>::N;
+    constexpr int kSelWant = (MODE != kSelect) ? 0 : (sizeof(T) == 4 ? AI_SEL_LDS_F32 : AI_SEL_LDS_F64);
+    // words selected from the kernel parameters: a multiple of the vector width (so the rest starts aligned)
+    constexpr int kSelNSel = (kSelWant <= 0) ? kSelN : ((kSelN - (kSelWant < kSelN ? kSelWant : kSelN)) / kSelPer * kSelPer);
+    constexpr int kSelStride = 20;           // elements per record in shared memory (fp32: 80 B = 5 chunks, fp64: 160 B)
+    __shared__ __align__(16) T sel_smem[(MODE == kSelect && kSelNSel < kSelN) ? 2 * kSelStride : 1];
+    if constexpr (MODE == kSelect && kSelNSel < kSelN) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < kSelStride; ++k) {
+                sel_smem[k] = (k < kSelN) ? sel.rec[0][k] : (T)0;
+                sel_smem[kSelStride + k] = (k < kSelN) ? sel.rec[1][k] : (T)0;
+            }
+        }
+        __syncthreads();
+    }
     auto load_record = [&](Record<BASIS, ORDER, T>& r, int leaf) {
         AI_CHECK(leaf >= 0 && leaf < (MODE == kSelect ? 2 : tv.n_records));   // kSelect: rec[1] == rec[0] for one leaf
         if constexpr (MODE == kSelect) {
 #pragma unroll
-            for (int k = 0; k < Record<BASIS, ORDER, T>::N; ++k) r.v[k] = leaf ? sel.rec[1][k] : sel.rec[0][k];
+            for (int k = 0; k < kSelNSel; ++k) r.v[k] = leaf ? sel.rec[1][k] : sel.rec[0][k];
+            if constexpr (kSelNSel < kSelN) {
+                const int4* sp = reinterpret_cast<const int4*>(sel_smem + leaf * kSelStride + kSelNSel);
+                constexpr int NV = (kSelN - kSelNSel + kSelPer - 1) / kSelPer;
+                T buf[NV * kSelPer];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int4 w = sp[q];
+                    if constexpr (sizeof(T) == 4) {
+                        buf[4 * q] = __int_as_float(w.x); buf[4 * q + 1] = __int_as_float(w.y);
+                        buf[4 * q + 2] = __int_as_float(w.z); buf[4 * q + 3] = __int_as_float(w.w);
+                    } else {
+                        buf[2 * q] = __hiloint2double(w.y, w.x); buf[2 * q + 1] = __hiloint2double(w.w, w.z);
+                    }
+                }
+#pragma unroll
+                for (int k = kSelNSel; k < kSelN; ++k) r.v[k] = buf[k - kSelNSel];
+            }
         } else {
             const T* p = records + leaf * R;
             if constexpr (VEC) r.load_vec(p);

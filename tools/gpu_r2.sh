@@ -49,6 +49,9 @@ ncu)
     ncu -i /tmp/prof_${name}.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/ncu_${tag}_${name}_source.csv.gz
     ls -la /tmp/prof_${name}.ncu-rep gpurun_out/ncu_${tag}_${name}_*
     ;;
+multi)
+    python tools/multi_bench.py --tag multi_${tag} > gpurun_out/multi_${tag}.txt 2>&1; cat gpurun_out/multi_${tag}.txt
+    ;;
 launches)
     python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/plain_launches.log 2>&1 || exit 1
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/ncu_l.log 2>&1

@@ -14,6 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
+    "sel_0_0": ["AI_SEL_LDS_F32=0", "AI_SEL_LDS_F64=0"],
+    "sel_4_4": ["AI_SEL_LDS_F32=4", "AI_SEL_LDS_F64=4"],
+    "sel_12_10": ["AI_SEL_LDS_F32=12", "AI_SEL_LDS_F64=10"],
+    "sel_16_16": ["AI_SEL_LDS_F32=16", "AI_SEL_LDS_F64=16"],
+}
+SEL_TABLES = "approx__32o13-p1.19209289551e-06,approx__64o13-p1.19209289551e-06,mx__cheb_o13_f32"
+
+VARIANTS = {
     "bin_t128_b4": ["AI_BIN_THREADS=128", "AI_BIN_MIN_BLOCKS=4"],
     "bin_t128_b5_np": ["AI_BIN_THREADS=128", "AI_BIN_MIN_BLOCKS=5", "AI_BIN_PREFETCH=0"],
     "bin_t128_b6_np": ["AI_BIN_THREADS=128", "AI_BIN_MIN_BLOCKS=6", "AI_BIN_PREFETCH=0"],
