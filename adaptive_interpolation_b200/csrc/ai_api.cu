@@ -1025,8 +1025,12 @@ int multi_entry(const ai_table* const* tabs, int m, const T* x, T* const* y, int
     // short (measured, profiles/r1_multi_table.txt: fp32 / fp64 order 6 gain 1.07-1.41x, fp64 order 13
     // on random points 0.95x), so long records take the per-table launches.  Test hook:
     // AI_B200_FORCE_FUSED_MULTI=1 fuses whenever the shapes allow it.
-    const bool short_records = (size_t)(t0->order + 1) * sizeof(T) <= 64 || std::getenv("AI_B200_FORCE_FUSED_MULTI");
-    bool fuse = (m >= 2) && short_records && !std::getenv("AI_B200_NO_FUSED_MULTI") && (ax % sizeof(T)) == 0;
+    // Two-leaf tables lose too (fp32 order 13, m = 2: 0.86x random, 0.97x sorted): alone they run
+    // the select kernel, fused they would gather from shared memory.
+    const bool forced_fuse = std::getenv("AI_B200_FORCE_FUSED_MULTI") != nullptr;
+    bool worth_fusing = (size_t)(t0->order + 1) * sizeof(T) <= 64;
+    for (int j = 0; j < m; ++j) worth_fusing = worth_fusing && tabs[j]->mode != ai::kSelect;
+    bool fuse = (m >= 2) && (worth_fusing || forced_fuse) && !std::getenv("AI_B200_NO_FUSED_MULTI") && (ax % sizeof(T)) == 0;
     size_t smem = 0;
     ai::MultiArgs args{};
     for (int j = 0; j < m && fuse; ++j) {

@@ -866,7 +866,7 @@ MULTI_GROUPS = [
     (["approx__64o7-p1.19209289551e-06", "approx__ci64o7-p1.19209289551e-06"], True),
     (["approx__32o7-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06"], True),
     (["approx__64o13-p1.19209289551e-06", "approx__ci64o13-p1.19209289551e-06"], "long"),  # two select-mode tables
-    (["approx__32o13-p1.19209289551e-06", "approx__ci32o13-p1.19209289551e-06"], True),
+    (["approx__32o13-p1.19209289551e-06", "approx__ci32o13-p1.19209289551e-06"], "long"),  # select-mode: per-table launches
     (["gen__j0_leg_o7_f32", "gen__cfg4_f1_leg_o7_f32"], False),                      # 99 leaves: bank mode
     (["approx__32o6-p1.19209289551e-06", "approx__32o7-p1.19209289551e-06"], False),  # orders differ
     (["gen__j0_mono_o5_f64", "gen__j0_mono_o5_f64"], True),

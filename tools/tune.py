@@ -36,6 +36,9 @@ VARIANTS = {
     "debug_bounds": ["AI_DEBUG_BOUNDS=1"],
     "packed_uniform_only": ["AI_PACKED_F32=2"],
     "packed_off": ["AI_PACKED_F32=0"],
+    # CTA shape: the same 16 warps per SM as two or four independent CTAs (round 2)
+    "blk256_mb2": ["AI_BLOCK=256", "AI_MIN_BLOCKS=2"],
+    "blk128_mb4": ["AI_BLOCK=128", "AI_MIN_BLOCKS=4"],
 }
 TABLES = ("approx__32o6-p1.19209289551e-06,approx__32o13-p1.19209289551e-06,gen__cfg3_j0_cheb_o13_f64,"
           "approx__64o7-p2.22044604925e-14,approx__64o6-p1.19209289551e-06,approx__32o3-p1.19209289551e-06")
@@ -45,7 +48,10 @@ def main():
     from adaptive_interpolation_b200 import build
     cmd = sys.argv[1] if len(sys.argv) > 1 else "build"
     if cmd == "build":
+        only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else list(VARIANTS)
         for tag, defs in VARIANTS.items():
+            if tag not in only:
+                continue
             print(tag, build.build(defines=defs, out="variant_%s.so" % tag))
         return
     tables = TABLES
