@@ -256,14 +256,17 @@ def pinned_empty(n, dtype):
     return arr
 
 
-def run_multi(x, ap, devices=None, timing="kernel"):
+def run_multi(x, ap, devices=None, timing="kernel", out=None):
     """generate.py:493-502 (the 'multi-threaded' launch).  Here: contiguous shards of the HOST array
     x over the given GPUs of this process (default: all visible), table replicated, no collective.
     One worker thread per device pushes its shard through the library's pinned, chunked
     H2D / kernel / D2H pipeline (ai_eval_host_*; the GIL is released during the call), so the copies
     of all devices overlap.  Returns (seconds, y): seconds is the max over devices of the summed
     kernel time (`timing="kernel"`, the reference's kernel-only convention, generate.py:484-489) or
-    the wall time of the whole call including every copy (`timing="wall"`)."""
+    the wall time of the whole call including every copy (`timing="wall"`).  `out` (optional): a
+    contiguous host array of x's size in the table dtype to receive y -- a pinned one
+    (`pinned_empty`) takes the D2H copies at full speed; by default a fresh pageable numpy array is
+    allocated, as `y_dev.get()` does upstream."""
     torch = _backend()
     import threading
     import time
@@ -276,7 +279,12 @@ def run_multi(x, ap, devices=None, timing="kernel"):
         return run_single(x, ap)            # already resident on one device
     dt = tables.table_dtype(ap)
     xa = np.ascontiguousarray(np.asarray(x), dtype=dt).reshape(-1)
-    out = np.empty_like(xa)
+    if out is None:
+        out = np.empty_like(xa)
+    elif not (isinstance(out, np.ndarray) and out.dtype == dt and out.flags.c_contiguous and out.size == xa.size):
+        raise Exception("out must be a contiguous %s array of x's size" % dt)
+    else:
+        out = out.reshape(-1)
     bounds = sharding.shard_bounds(xa.size, len(devices))
     tabs = [device_table(ap, d) for d in devices]          # created before the clock starts
     kernel_ms = [0.0] * len(devices)

@@ -631,6 +631,11 @@ def test_run_multi_uses_the_pinned_pipeline_and_reports_wall_time():
     assert sec_w >= sec_k * 0.5 and np.array_equal(out, want)
     sec_1, out = generate.run_multi(x, ap, devices=[0])
     assert np.array_equal(out, want)
+    y = generate.pinned_empty(n, np.float32)                   # caller-provided (pinned) output
+    sec_p, out = generate.run_multi(x, ap, out=y)
+    assert out.ctypes.data == y.ctypes.data and np.array_equal(y, want)
+    with pytest.raises(Exception):
+        generate.run_multi(x, ap, out=np.empty(n, dtype=np.float64))
     with pytest.raises(Exception):
         generate.run_multi(x, ap, timing="cpu")
 
