@@ -14,7 +14,8 @@ import golden_io  # noqa: E402  (fixture loader, tests/golden/golden_io.py)
 TABLES = ["approx__32o6-p1.19209289551e-06", "approx__32o3-p1.19209289551e-06", "gen__cfg4_f1_leg_o7_f32",
           "gen__cfg4_f1_leg_o7_f64", "approximations__64o5-p2.22044604925e-14", "gen__j0_mono_o13_f64",
           "gen__cfg3_j0_cheb_o13_f64", "gen__line1_mono_o1_f64", "approx__64o13-p1.19209289551e-06",
-          "approx__64o7-p2.22044604925e-14", "approx__32o7-p1.19209289551e-06"]
+          "approx__64o7-p2.22044604925e-14", "approx__32o7-p1.19209289551e-06",
+          "large__approx__64o3-p2.22044604925e-15", "mx__cheb_o3_f64", "mx__leg_o13_f32", "trim__j0_cheb_o6_f64"]
 
 
 def child():
@@ -49,12 +50,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for mode in (None, "0", "1", "2", "3", "4", "nohdr", "nocell"):
+        for mode in (None, "0", "1", "2", "3", "4", "9", "10", "nohdr", "nocell", "norank"):
             env = dict(os.environ)
             if mode == "nohdr":
                 env["AI_B200_NO_PACKED_HDR"] = env["AI_B200_NO_UNIFORM_HDR"] = "1"
             elif mode == "nocell":
                 env["AI_B200_NO_CELL_RECORDS"] = env["AI_B200_NO_UNIFORM_HDR"] = "1"
+            elif mode == "norank":
+                env["AI_B200_NO_RANK"] = "1"
             elif mode is not None:
                 env["AI_B200_FORCE_MODE"] = mode
             r = subprocess.run([sys.executable, __file__, "child"], env=env)
