@@ -660,6 +660,20 @@ bool build_compact_image(ai_table* t, const GridPlan& gp, std::vector<unsigned c
     return true;
 }
 
+// what build_image / build_compact_image write into the table, to put it back when a layout is
+// built but not taken
+struct SavedPlan {
+    int rstride, packed, uniform_hdr, rank16, cell_records, compact;
+    ai::TableView view;
+    explicit SavedPlan(const ai_table* t)
+        : rstride(t->rstride), packed(t->packed), uniform_hdr(t->uniform_hdr), rank16(t->rank16),
+          cell_records(t->cell_records), compact(t->compact), view(t->view) {}
+    void restore(ai_table* t) const {
+        t->rstride = rstride; t->packed = packed; t->uniform_hdr = uniform_hdr; t->rank16 = rank16;
+        t->cell_records = cell_records; t->compact = compact; t->view = view;
+    }
+};
+
 int prepare_dispatch(int basis, int dtype, int order, int mode, int smem, int* bps) {
     cudaError_t e = cudaErrorInvalidValue;
     if (dtype == AI_DTYPE_F32) {
@@ -716,7 +730,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
                                                          : plan_uniform_header<double>(t, gp);
     const size_t esz = (t->dtype == AI_DTYPE_F32) ? 4 : 8;
     const int full_copies = (t->dtype == AI_DTYPE_F32) ? 32 : 16;
-    int mode = ai::kSmem, copies = 1, bcopies = 1;
+    int mode = ai::kSmem, copies = 1, bcopies = 1, vc_smem = 0;
     bool go_global = false;
     // First with one record per coarse cell (when the grid allows it); kept only if the gathers
     // stay conflict-free -- packed with one record per bank, or fully replicated.  Otherwise
@@ -814,6 +828,32 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         if (soff_r) *soff_r = (int)orr;
         return orr + (size_t)round_up16((size_t)t->view.n_records_elems * esz * cp);
     };
+    // Eight-copy layout of a DYADIC table: the compact cell records (no header words, no rank lookup)
+    // when their eight copies fit -- 429-leaf 64o5: 3 loads per point instead of 4 + a rank word.
+    if ((mode == ai::kSmemV && forced < 0 && !std::getenv("AI_B200_NO_COMPACT") && !std::getenv("AI_B200_NO_CELL_RECORDS"))
+        || (forced == ai::kSmemVC && !go_global && !std::getenv("AI_B200_NO_CELL_RECORDS"))) {
+        GridPlan gpx;
+        std::vector<unsigned char> image_c;
+        const SavedPlan saved(t);
+        if (plan_grid(t->breaks, t->dtype, &gpx, kGridMaxLarge) == AI_OK) {
+            const bool ok = (t->dtype == AI_DTYPE_F32) ? build_compact_image<float>(t, gpx, &image_c)
+                                                       : build_compact_image<double>(t, gpx, &image_c);
+            const int nv = ai::rec_stride_vc(t->order, (int)esz) * (int)esz / 16;
+            const size_t need = (size_t)t->view.aux_bytes + (size_t)t->view.n_records * nv * 16 * ai::kVecCopies;
+            if (ok && need <= smem_cap) {
+                image.swap(image_c);
+                gp = gpx;
+                t->G = gp.G; t->p = gp.p; t->K = gp.K; t->g0 = gp.g0;
+                mode = ai::kSmemVC; compact = true;
+                copies = nv;                                                   // chunks per shared-memory record
+                bcopies = ai::rec_stride_compact(t->order, (int)esz) * (int)esz / 16;   // chunks per global record
+                t->view.soff_records = t->view.aux_bytes;
+                vc_smem = (int)need;
+            } else {
+                saved.restore(t);
+            }
+        }
+    }
     if (mode == ai::kSmemV) {
         // the records in the 16-byte padded global layout ([a, 2/(b-a), c0..cn, pad]), one per leaf
         rc = (t->dtype == AI_DTYPE_F32) ? build_image<float>(t, gp, true, &image, nullptr, false)
@@ -854,6 +894,7 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->smem_resident = (mode != ai::kGlobal && mode != ai::kGlobalC);
     t->eval_smem = 0;
     if (mode == ai::kGlobalC) t->eval_smem = t->view.aux_bytes;
+    if (mode == ai::kSmemVC) t->eval_smem = vc_smem;
     if (mode == ai::kSmem || mode == ai::kSmemP || mode == ai::kSmemU) t->eval_smem = t->view.image_bytes;
     if (mode == ai::kSmemV) {
         t->view.soff_breaks = t->view.off_breaks;
@@ -862,7 +903,8 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     } else if (ai::mode_bank(mode)) {
         t->eval_smem = (int)bank_layout(copies, &t->view.soff_breaks, &t->view.soff_records);
     }
-    t->aux_smem = (mode == ai::kGlobal) ? 0 : (mode == ai::kGlobalC ? t->view.aux_bytes : t->view.image_bytes);
+    t->aux_smem = (mode == ai::kGlobal) ? 0
+                  : ((mode == ai::kGlobalC || mode == ai::kSmemVC) ? t->view.aux_bytes : t->view.image_bytes);
     t->view.image = nullptr;
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
@@ -904,7 +946,13 @@ int finish_table(ai_table* t) {
     rc = prepare_dispatch(t->basis, t->dtype, t->order, t->mode, t->eval_smem, &bps);
     if (rc) return rc;
     if (bps < 1) return fail(AI_ERR_CUDA, "kernel does not fit on an SM with %d B of shared memory", t->eval_smem);
-    if (t->mode != ai::kGlobal && t->mode != ai::kSmemV && t->mode != ai::kGlobalC && t->aux_smem > 48 * 1024) {
+    if (t->mode == ai::kSmemVC) {
+        int dummy = 0;      // its reduction runs the kGlobalC kernel on the same image
+        rc = prepare_dispatch(t->basis, t->dtype, t->order, ai::kGlobalC, t->aux_smem, &dummy);
+        if (rc) return rc;
+    }
+    if (t->mode != ai::kGlobal && t->mode != ai::kSmemV && t->mode != ai::kGlobalC && t->mode != ai::kSmemVC
+        && t->aux_smem > 48 * 1024) {
         int dummy = 0;      // opt the reduction kernel (packed layout) into large shared memory too
         rc = prepare_dispatch(t->basis, t->dtype, t->order,
                               t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem), t->aux_smem, &dummy);
@@ -1091,7 +1139,7 @@ int index_entry(const ai_table* t, const T* x, int32_t* idx, int64_t n, void* st
     if (!guard.ok) return fail(AI_ERR_CUDA, "cannot select device %d", t->device);
     const long long want = (n + ai::kBlock - 1) / ai::kBlock;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)t->sm_count * 2));
-    if (t->mode == ai::kGlobal || t->mode == ai::kGlobalC) {
+    if (t->mode == ai::kGlobal || t->mode == ai::kGlobalC || t->mode == ai::kSmemVC) {
         ai::index_kernel<T, ai::kGlobal><<<grid, ai::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(t->view, x, idx, n);
     } else {
         if (t->aux_smem > 48 * 1024) {
@@ -1129,7 +1177,7 @@ int sum_entry(const ai_table* t, const T* x, double* result, int64_t n, void* st
     const bool from_global = t->mode == ai::kGlobal || t->mode == ai::kSmemV;
     if (from_global) cfg.smem_bytes = 0;
     const int m = from_global ? ai::kGlobal
-                              : (t->mode == ai::kGlobalC ? ai::kGlobalC
+                              : ((t->mode == ai::kGlobalC || t->mode == ai::kSmemVC) ? ai::kGlobalC
                                  : (t->uniform_hdr ? ai::kSmemU : (t->packed ? ai::kSmemP : ai::kSmem)));
     if constexpr (sizeof(T) == 4) {
         if (t->basis == ai::kCheb) e = ai::launch_sum_cheb_f32(t->order, m, cfg, t->view, x, result, n);

@@ -83,6 +83,7 @@ struct Switch {
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::eval(a...);
             if (mode == kSmemV) return Unit<BASIS, T, ORDER, kSmemV>::eval(a...);
             if (mode == kGlobalC) return Unit<BASIS, T, ORDER, kGlobalC>::eval(a...);
+            if (mode == kSmemVC) return Unit<BASIS, T, ORDER, kSmemVC>::eval(a...);
             if constexpr (BASIS != kMono) {          // the monomial record has no header to pack
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::eval(a...);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::eval(a...);
@@ -129,6 +130,7 @@ struct Switch {
             if (mode == kSelect) return Unit<BASIS, T, ORDER, kSelect>::prepare(smem_bytes, bps);
             if (mode == kSmemV) return Unit<BASIS, T, ORDER, kSmemV>::prepare(smem_bytes, bps);
             if (mode == kGlobalC) return Unit<BASIS, T, ORDER, kGlobalC>::prepare(smem_bytes, bps);
+            if (mode == kSmemVC) return Unit<BASIS, T, ORDER, kSmemVC>::prepare(smem_bytes, bps);
             if constexpr (BASIS != kMono) {
                 if (mode == kSmemP) return Unit<BASIS, T, ORDER, kSmemP>::prepare(smem_bytes, bps);
                 if (mode == kSmemBankP) return Unit<BASIS, T, ORDER, kSmemBankP>::prepare(smem_bytes, bps);

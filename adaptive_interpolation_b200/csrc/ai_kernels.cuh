@@ -115,8 +115,13 @@ enum : int { kCheb = 0, kLeg = 1, kMono = 2 };
 //              leaf's first cell (cell with its low k bits cleared), a = fma(first cell, w, lb) and
 //              2/(b-a) = S1 * 2^-k -- all verified bit for bit on the host.  No grid table, no
 //              breakpoints and no header words are read: one global access per point instead of 5-6.
+//   kSmemVC    kSmemV for DYADIC tables: the headerless cell records of kGlobalC ([c0..cn] padded to 16
+//              bytes, one per coarse cell) in eight 128-bit copies, the 4-bit levels beside them;
+//              header computed as in kGlobalC.  An order-5 fp64 record is 3 loads instead of 4 and
+//              the cell index addresses it directly (no rank lookup).  The global image IS the
+//              kGlobalC image (the index and reduction kernels read it as such).
 enum : int { kSmem = 0, kSmemBank = 1, kGlobal = 2, kSmemBankN = 3, kSelect = 4, kSmemP = 5, kSmemBankP = 6,
-             kSmemU = 7, kSmemBankU = 8, kSmemV = 9, kGlobalC = 10 };
+             kSmemU = 7, kSmemBankU = 8, kSmemV = 9, kGlobalC = 10, kSmemVC = 11 };
 constexpr int kVecCopies = 8;
 __host__ __device__ constexpr bool mode_packed_hdr(int mode) { return mode == kSmemP || mode == kSmemBankP; }
 __host__ __device__ constexpr bool mode_uniform_hdr(int mode) { return mode == kSmemU || mode == kSmemBankU; }
@@ -192,11 +197,17 @@ __host__ __device__ constexpr int rec_stride_compact(int order, int elem_bytes) 
     const int per = 32 / elem_bytes;
     return (order + 1 + per - 1) / per * per;
 }
+// kSmemVC: [c0..cn] padded to 16 bytes (shared-memory copy of the kGlobalC records)
+__host__ __device__ constexpr int rec_stride_vc(int order, int elem_bytes) {
+    const int per = 16 / elem_bytes;
+    return (order + 1 + per - 1) / per * per;
+}
 // packed header (kSmemP / kSmemBankP): [a|j, c0..cn]
 __host__ __device__ constexpr int rec_stride_packed(int order) { return ((order + 2) | 1); }
 template <int BASIS, int ORDER, typename T, int MODE>
 __host__ __device__ constexpr int rec_stride_for() {
-    return MODE == kGlobalC ? rec_stride_compact(ORDER, (int)sizeof(T))
+    return MODE == kSmemVC ? rec_stride_vc(ORDER, (int)sizeof(T))
+           : MODE == kGlobalC ? rec_stride_compact(ORDER, (int)sizeof(T))
            : (MODE == kGlobal || MODE == kSmemV) ? rec_stride_global(BASIS, ORDER, (int)sizeof(T))
                            : (mode_packed_hdr(MODE) ? rec_stride_packed(ORDER)
                                                     : (mode_uniform_hdr(MODE) ? rec_stride(kMono, ORDER) : rec_stride(BASIS, ORDER)));
@@ -490,6 +501,34 @@ template <int BASIS, int ORDER, typename T> struct Record {
             else v[1] = __hiloint2double((int)(s1_hi - (k << 20)), (int)s1_lo);
         }
     }
+    // kSmemVC: the same headerless record from this lane's shared-memory copy (chunk q sits
+    // kVecCopies chunks after chunk q - 1), header computed as in load_compact
+    __device__ __forceinline__ void load_compact_smem(const T* __restrict__ rec, unsigned cell, unsigned k, T w, T lb,
+                                                      unsigned s1_hi, unsigned s1_lo) {
+        constexpr int C = ORDER + 1;
+        constexpr int PER = 16 / (int)sizeof(T);
+        constexpr int NV = (C + PER - 1) / PER;
+        const int4* p = reinterpret_cast<const int4*>(rec);
+        T buf[NV * PER];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int4 v4 = p[q * kVecCopies];
+            if constexpr (sizeof(T) == 4) {
+                buf[4 * q] = __int_as_float(v4.x); buf[4 * q + 1] = __int_as_float(v4.y);
+                buf[4 * q + 2] = __int_as_float(v4.z); buf[4 * q + 3] = __int_as_float(v4.w);
+            } else {
+                buf[2 * q] = __hiloint2double(v4.y, v4.x); buf[2 * q + 1] = __hiloint2double(v4.w, v4.z);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < C; ++j) v[HDR + j] = buf[j];
+        if constexpr (HDR == 2) {
+            const unsigned first_cell = cell & (0xffffffffu << k);
+            v[0] = fma_((T)(int)first_cell, w, lb);
+            if constexpr (sizeof(T) == 4) v[1] = __uint_as_float(s1_hi - (k << 23));
+            else v[1] = __hiloint2double((int)(s1_hi - (k << 20)), (int)s1_lo);
+        }
+    }
     // 16-byte aligned record in global memory: 128-bit read-only loads
     __device__ __forceinline__ void load_vec(const T* __restrict__ rec) {
         constexpr int PER = 16 / (int)sizeof(T);
@@ -675,6 +714,24 @@ template <typename T, int MODE>
 __device__ __forceinline__ const unsigned char* table_base(const TableView& tv, unsigned char* smem) {
     if constexpr (MODE == kGlobal || MODE == kSelect) {
         return tv.image;
+    } else if constexpr (MODE == kSmemVC) {
+        // levels at the front, then every 16-byte chunk of every (32-byte padded) global record that
+        // holds coefficients, written kVecCopies times chunk-interleaved
+        const int4* asrc = reinterpret_cast<const int4*>(tv.image + tv.off_aux);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int k = threadIdx.x; k < tv.aux_bytes / 16; k += blockDim.x) dst[k] = __ldg(asrc + k);
+        const int4* rsrc = reinterpret_cast<const int4*>(tv.image + tv.off_records);
+        int4* rdst = reinterpret_cast<int4*>(smem + tv.soff_records);
+        const int nv = tv.copies;                       // 16-byte chunks per shared-memory record
+        const int gchunks = tv.bcopies;                 // 16-byte chunks per global record
+        const int total = tv.n_records * nv * kVecCopies;
+        for (int k = threadIdx.x; k < total; k += blockDim.x) {
+            const int chunk = k / kVecCopies;           // (record, q)
+            const int rec = chunk / nv, q = chunk - rec * nv;
+            rdst[k] = __ldg(rsrc + rec * gchunks + q);
+        }
+        __syncthreads();
+        return smem;
     } else if constexpr (MODE == kGlobalC) {
         // only the 4-bit levels are staged; grid table and records stay in global memory
         const int4* src = reinterpret_cast<const int4*>(tv.image + tv.off_aux);
@@ -732,13 +789,14 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     constexpr bool VEC = (MODE == kGlobal);                        // 128-bit record loads
     constexpr bool PK = mode_packed_hdr(MODE);                     // one-element record header
     // copies per record element: compile-time except in kSmemBankN
-    const int cp = (MODE == kSmemBankN) ? tv.copies : (MODE == kSmemV ? kVecCopies : Copies<T, MODE>::value);
+    const int cp = (MODE == kSmemBankN) ? tv.copies
+                   : ((MODE == kSmemV || MODE == kSmemVC) ? kVecCopies : Copies<T, MODE>::value);
     // record stride in elements (kSmemBankN: packed or unpacked header, decided per table)
     const int R = ((MODE == kSmemBankN && Record<BASIS, ORDER, T>::HDR == 2 && tv.s0_hi)
                        ? rec_stride_packed(ORDER) : rec_stride_for<BASIS, ORDER, T, MODE>()) * cp;
     // bank-private layout: lane l reads copy l mod cp of every element (kSmemV: of every 16-byte chunk)
-    const T* records = reinterpret_cast<const T*>(base + (kBank ? tv.soff_records : tv.off_records))
-                       + (threadIdx.x & (cp - 1)) * (MODE == kSmemV ? 16 / (int)sizeof(T) : 1);
+    const T* records = reinterpret_cast<const T*>(base + ((kBank || MODE == kSmemVC) ? tv.soff_records : tv.off_records))
+                       + (threadIdx.x & (cp - 1)) * ((MODE == kSmemV || MODE == kSmemVC) ? 16 / (int)sizeof(T) : 1);
     if constexpr (kBank) lk.use_replicated_breaks(tv, base);
     const T inv_order = (T)tv.inv_order;
 
@@ -793,6 +851,11 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
                 if constexpr (Record<BASIS, ORDER, T>::HDR == 2) k = (smem[leaf >> 1] >> ((leaf & 1) * 4)) & 15u;
                 r.load_compact(p, (unsigned)leaf, k, (T)tv.u_w, (T)tv.u_lb, tv.s0_hi, tv.s0_lo);
             }
+            else if constexpr (MODE == kSmemVC) {
+                unsigned k = 0;
+                if constexpr (Record<BASIS, ORDER, T>::HDR == 2) k = (smem[leaf >> 1] >> ((leaf & 1) * 4)) & 15u;
+                r.load_compact_smem(p, (unsigned)leaf, k, (T)tv.u_w, (T)tv.u_lb, tv.s0_hi, tv.s0_lo);
+            }
             else if constexpr (MODE == kSmemV) r.load_vec_smem(p);
             else if constexpr (PK) r.template load_packed<Copies<T, MODE>::value>(p, tv.s0_hi, tv.s0_lo);
             else if constexpr (mode_uniform_hdr(MODE))
@@ -817,7 +880,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
         if constexpr (MODE == kSelect) {
 #pragma unroll
             for (int e = 0; e < (int)(sizeof(li) / sizeof(li[0])); ++e) li[e] = !(xs[e] < sel.mid) ? 1 : 0;
-        } else if constexpr (MODE == kGlobalC) {                   // one record per coarse cell, wide division
+        } else if constexpr (MODE == kGlobalC || MODE == kSmemVC) {   // one record per coarse cell, wide division
 #pragma unroll
             for (int e = 0; e < (int)(sizeof(li) / sizeof(li[0])); ++e) li[e] = (int)lk.coarse_cell_wide(xs[e]);
         } else {
@@ -827,7 +890,7 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     auto f = [&](T xv) -> T {
         Record<BASIS, ORDER, T> r;
         if constexpr (MODE == kSelect) load_record(r, !(xv < sel.mid) ? 1 : 0);
-        else if constexpr (MODE == kGlobalC) load_record(r, (int)lk.coarse_cell_wide(xv));
+        else if constexpr (MODE == kGlobalC || MODE == kSmemVC) load_record(r, (int)lk.coarse_cell_wide(xv));
         else load_record(r, lk.leaf(xv));
         return eval_record<BASIS, ORDER, T>(r, xv, inv_order);
     };

@@ -31,7 +31,10 @@ def test_plan_is_consistent(name):
     assert info["lower_bound"] == float(f.breaks[0]) and info["upper_bound"] == float(f.breaks[-1])
     assert 1 <= info["grid_cells"] <= (1 << 20)
     assert info["smem_bytes"] <= 227 * 1024
-    assert info["residency"] in (0, 1, 2, 3, 4, 9, 10)
+    assert info["residency"] in (0, 1, 2, 3, 4, 9, 10, 11)
+    if info["residency"] == 11:                        # eight 128-bit copies of headerless cell records
+        assert info["cell_records"] == 1 and info["search_steps"] == 0 and info["smem_resident"] == 1
+        assert f.n_leaves > (32 if f.dtype == np.float32 else 16)
     if info["residency"] == 10:                        # compact L2-resident layout: headerless 32-byte cell records
         assert info["cell_records"] == 1 and info["search_steps"] == 0 and info["smem_resident"] == 0
         assert info["record_stride"] * f.dtype.itemsize % 32 == 0 and info["smem_bytes"] <= 64 * 1024
@@ -45,7 +48,7 @@ def test_plan_is_consistent(name):
         assert f.n_leaves > (32 if f.dtype == np.float32 else 16)
     if info["lookup_mode"] in (2, 3):                  # rank from a register bitmap / from rank words
         assert info["search_steps"] == 0
-    hdr = 0 if (f.basis == "monomial" or info["residency"] == 10) else {0: 2, 1: 1, 2: 0}[info["header_packed"]]
+    hdr = 0 if (f.basis == "monomial" or info["residency"] in (10, 11)) else {0: 2, 1: 1, 2: 0}[info["header_packed"]]
     assert info["record_stride"] >= f.order + 1 + hdr
 
 
@@ -54,16 +57,16 @@ def test_saved_tables_plan():
     for name in SAVED:
         info = plan(name)
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
-        assert info["header_packed"] in (1, 2) or info["residency"] == 9, (name, info)
+        assert info["header_packed"] in (1, 2) or info["residency"] in (9, 11), (name, info)
         assert info["image_bytes"] <= 48 * 1024, (name, info)
     assert plan("approx__32o6-p1.19209289551e-06")["lookup_mode"] == 2          # BASELINE configs[1]
     assert plan("approx__32o6-p1.19209289551e-06")["residency"] == 0
     assert plan("approx__32o3-p1.19209289551e-06")["residency"] == 1            # 62 leaves > 32 banks
     assert plan("approx__64o13-p1.19209289551e-06")["residency"] == 4           # two leaves: select
     big = plan("approximations__64o5-p2.22044604925e-14")                       # 429 leaves
-    # full per-bank replication (16 copies) does not fit: 8 copies of 64-byte records, 128-bit loads,
-    # and the leaf from rank words instead of a 1 KB first[] table
-    assert big["residency"] == 9 and big["bank_copies"] == 8 and big["lookup_mode"] == 3
+    # full per-bank replication (16 copies) does not fit: 8 copies of headerless 48-byte cell records
+    # (the table is dyadic), 128-bit loads, the header from 4-bit levels
+    assert big["residency"] == 11 and big["cell_records"] == 1 and big["smem_bytes"] <= 227 * 1024
 
 
 def test_config_tables_plan():
@@ -99,12 +102,16 @@ def test_hooks(monkeypatch):
     info = plan(name)
     assert info["grid_cells"] <= 8 and info["search_steps"] >= 1 and info["lookup_mode"] == 1
     monkeypatch.delenv("AI_B200_MAX_CELLS")
-    for mode in (0, 1, 2, 9, 10):
+    for mode in (0, 1, 2, 9, 10, 11):
         monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
         assert plan(name)["residency"] == mode
     monkeypatch.delenv("AI_B200_FORCE_MODE")
     monkeypatch.setenv("AI_B200_NO_VEC_MODE", "1")
     assert plan("approximations__64o5-p2.22044604925e-14")["residency"] == 3     # the partial-copy layout it replaces
+    monkeypatch.delenv("AI_B200_NO_VEC_MODE")
+    monkeypatch.setenv("AI_B200_NO_COMPACT", "1")
+    info = plan("approximations__64o5-p2.22044604925e-14")                       # eight copies WITH [a, s] and rank words
+    assert info["residency"] == 9 and info["bank_copies"] == 8 and info["lookup_mode"] == 3
 
 
 def test_large_tables_plan():
