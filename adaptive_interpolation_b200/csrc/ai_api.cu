@@ -1552,7 +1552,7 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
                       : ((t->mode == ai::kSmemBankP || t->mode == ai::kSmemBankU) ? ai::kSmemBank : t->mode);
     info->header_packed = t->uniform_hdr ? 2 : t->packed;
     info->cell_records = t->cell_records;
-    info->bank_copies = t->copies;
+    info->bank_copies = (t->mode == ai::kSmemVC) ? ai::kVecCopies : t->copies;
     info->smem_resident = t->smem_resident;
     info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : (t->rank16 ? 3 : 0));
     info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;

@@ -34,7 +34,7 @@ def test_plan_is_consistent(name):
     assert info["residency"] in (0, 1, 2, 3, 4, 9, 10, 11)
     if info["residency"] == 11:                        # eight 128-bit copies of headerless cell records
         assert info["cell_records"] == 1 and info["search_steps"] == 0 and info["smem_resident"] == 1
-        assert f.n_leaves > (32 if f.dtype == np.float32 else 16)
+        assert info["bank_copies"] == 8
     if info["residency"] == 10:                        # compact L2-resident layout: headerless 32-byte cell records
         assert info["cell_records"] == 1 and info["search_steps"] == 0 and info["smem_resident"] == 0
         assert info["record_stride"] * f.dtype.itemsize % 32 == 0 and info["smem_bytes"] <= 64 * 1024

@@ -54,3 +54,22 @@ def test_two_gloo_ranks(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("n", [0, 1, 511, 512, 100003, 1 << 20, 1 << 30])
+def test_shard_bounds_cover_the_array(n, world):
+    """bench.py's strong-scaled configs (BASELINE configs[2] / [4]: 2^30 GLOBAL points over the N
+    GPUs) and generate.run_multi split one array with sharding.shard_bounds: contiguous, disjoint,
+    covering, interior boundaries on multiples of 512 elements (every shard keeps the 16-byte vector
+    path), and equal shards whenever the size allows."""
+    from adaptive_interpolation_b200 import sharding
+    b = sharding.shard_bounds(n, world)
+    assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(b, b[1:]):
+        assert lo <= hi == lo2
+    for lo, hi in b[:-1]:
+        assert hi % 512 == 0 or n < 512 * world
+    if n == 1 << 30 and world in (1, 2, 4, 8):
+        assert all(hi - lo == n // world for lo, hi in b)
+    assert [sharding.shard_of(n, r, world) for r in range(world)] == b
