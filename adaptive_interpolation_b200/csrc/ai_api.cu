@@ -716,6 +716,10 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
         if (kb >= 16 && (size_t)kb * 1024 < smem_cap) smem_cap = (size_t)kb * 1024;
     }
 
+    // (the kernels also hold a few bytes of static shared memory: keep a margin below the opt-in limit
+    // so that a table planned at the very edge cannot fail to launch)
+    if (smem_cap > 1024) smem_cap -= 256;
+
     // Build the shared-memory image first -- with the one-word record header when every leaf
     // qualifies (bit-identical values, one shared-memory wavefront less per 32 points, two in
     // fp64, and a shorter record) -- and if it cannot be staged rebuild it in the global layout

@@ -319,6 +319,56 @@ def test_large_table_is_l2_resident(n_leaves, lo, hi, dtype, expect_k0):
     assert np.all(np.abs(y[fin].astype(np.float64) - y_o[fin]) <= value_tolerance(dtype, scale[fin], GPU_ULPS))
 
 
+def _bisection_breaks(n_leaves, lo, hi, dtype, seed):
+    """Breakpoints of a random bisection tree with n_leaves leaves on [lo, hi] (what the reference's
+    adaptive fitter builds: every split halves a leaf), depth capped so the table stays dyadic."""
+    rng = np.random.default_rng(seed)
+    leaves = [(0, 0)]                                     # (index at its depth, depth): interval [i, i+1) / 2^d
+    while len(leaves) < n_leaves:
+        j = int(rng.integers(0, len(leaves)))
+        i, d = leaves[j]
+        if d >= 14:
+            continue
+        leaves[j:j + 1] = [(2 * i, d + 1), (2 * i + 1, d + 1)]
+    edges = sorted({i / 2.0 ** d for i, d in leaves} | {1.0})
+    return (lo + (hi - lo) * np.array(edges)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("order", [3, 7, 13])
+def test_tables_around_the_shared_memory_capacity(order, dtype):
+    """Tables from a few hundred to a few thousand leaves, uniform and bisection-shaped, cross every
+    residency boundary (per-bank copies / eight copies / compact eight copies / L2-resident compact):
+    each must be planned into a launchable layout and evaluate like the oracle, indices exact."""
+    seen = set()
+    for n_leaves in (200, 430, 700, 1000, 1500, 2400, 5000):
+        for shape in ("uniform", "bisection"):
+            if shape == "uniform":
+                f = _synthetic_table(n_leaves, 0.0, 16.0, order, dtype, 0)      # 16 / n: dyadic only for powers of two
+            else:
+                br = _bisection_breaks(n_leaves, 0.0, 16.0, dtype, n_leaves)
+                coef = np.random.default_rng(n_leaves).standard_normal((len(br) - 1, order + 1)).astype(dtype)
+                f = tables.FlatTable("chebyshev", order, dtype, br, coef)
+            tab = tables.DeviceTable(f, 0)
+            info = tab.info()
+            seen.add(info["residency"])
+            assert info["smem_bytes"] <= 227 * 1024 and info["blocks_per_sm"] >= 1, info
+            rng = np.random.default_rng(3)
+            inf = dtype(np.inf)
+            x = np.concatenate([f.breaks, np.nextafter(f.breaks, -inf), np.nextafter(f.breaks, inf),
+                                rng.uniform(-1.0, 17.0, 1 << 16).astype(dtype)])
+            y_o, idx_o, _ = oracle_np.evaluate(f.breaks, f.coef, f.basis, f.order, x, want_cond=True)
+            assert np.array_equal(gpu_index(tab, x), idx_o), (n_leaves, shape, info)
+            y = gpu_eval(tab, x)
+            scale = oracle_np.error_scale(f.breaks, f.coef, f.basis, f.order, x)
+            fin = np.isfinite(y_o) & np.isfinite(scale)
+            assert np.all(np.abs(y[fin].astype(np.float64) - y_o[fin]) <= value_tolerance(dtype, scale[fin], GPU_ULPS)), \
+                (n_leaves, shape, info)
+            tab.close()
+    report(test="capacity_edges", order=order, dtype=np.dtype(dtype).name, residencies=sorted(seen))
+    assert len(seen) >= 3, seen
+
+
 def _random_breaks(rng, dtype, kind):
     """Sorted, strictly increasing breakpoints of assorted nastiness."""
     L = int(rng.integers(1, 300))

@@ -89,6 +89,21 @@ def main():
             vals = np.sin(3 * (mids[:, None] + half[:, None] * nodes[None, :]))
             co = np.stack([C.chebfit(nodes, v, order) for v in vals]).astype(dt)
             f = tables.FlatTable("chebyshev", order, dt, br, co)
+        elif name.startswith("bisect:"):
+            # bisect:<leaves>:<order>:<f32|f64>  -- a random bisection tree on [0,16] (depth <= 14: dyadic),
+            # the shape the reference's adaptive fitter produces; random coefficients
+            _, nl, order, tname = name.split(":")
+            nl, order, dt = int(nl), int(order), (np.float32 if tname == "f32" else np.float64)
+            rng = np.random.default_rng(nl)
+            leaves = [(0, 0)]
+            while len(leaves) < nl:
+                j = int(rng.integers(0, len(leaves)))
+                i, d = leaves[j]
+                if d < 14:
+                    leaves[j:j + 1] = [(2 * i, d + 1), (2 * i + 1, d + 1)]
+            edges = sorted({i / 2.0 ** d for i, d in leaves} | {1.0})
+            br = (16.0 * np.array(edges)).astype(dt)
+            f = tables.FlatTable("chebyshev", order, dt, br, rng.standard_normal((len(br) - 1, order + 1)).astype(dt))
         else:
             g = golden_io.load_golden(name)
             f = tables.flatten(g)
