@@ -596,6 +596,23 @@ def test_eval_host_pipeline(name, n):
         _cabi.check(_cabi.lib().ai_host_free(p))
 
 
+def test_host_roundtrip_measurement_leaves_the_pipeline_usable():
+    """ai_measure_host_roundtrip (the plain-copy ceiling bench.py reports beside e2e): same chunks,
+    slots and streams as ai_eval_host_*, no kernel; must not disturb a following evaluation."""
+    g = golden("approx__32o6-p1.19209289551e-06")
+    tab = dev_table(g.name)
+    n = (1 << 24) + 5
+    x = generate.pinned_empty(n, np.float32)
+    x[:] = np.random.default_rng(4).uniform(0, 20, n).astype(np.float32)
+    y = generate.pinned_empty(n, np.float32)
+    L = _cabi.lib()
+    assert L.ai_measure_host_roundtrip(tab.handle, x.ctypes.data, y.ctypes.data, n) == 0
+    assert L.ai_measure_host_roundtrip(tab.handle, x.ctypes.data, y.ctypes.data, 0) == 0
+    assert L.ai_measure_host_roundtrip(None, x.ctypes.data, y.ctypes.data, n) == 1
+    out, ms = tab.eval_host(x, y)
+    assert ms > 0 and np.array_equal(out, gpu_eval(tab, x))
+
+
 def test_eval_sum_variant():
     """The reference's no-"output" kernel variant (generate.py:392-394): y reduced, not stored."""
     for name in ("approx__32o6-p1.19209289551e-06", "gen__cfg3_j0_cheb_o13_f64",
@@ -731,6 +748,9 @@ def test_staged_table_follows_the_tree_content():
     ap.interval_a = None
     assert generate.device_table(ap) is not t0
     assert not np.array_equal(generate.run(x, ap), y0)
+    t1 = generate.device_table(ap)
+    generate.invalidate(ap)                       # the documented way after editing tree_1d IN PLACE
+    assert generate.device_table(ap) is not t1
 
 
 def test_integration_stub_pure_ctypes():
