@@ -626,6 +626,10 @@ def main():
                             "order": flat.order, "leaves": flat.n_leaves, "value": value, "unit": UNIT, "steps": args.steps,
                             "kernel_ms": kernel_ms, "kernel_ms_min": kernel_ms_min, "frac": achieved / hbm,
                             "clocks": headline_clocks, "note": "the headline line above"})
+            # the headline table on the reference's OWN input order: a sorted linspace (run_test.py:230-235)
+            rec = run_config("cfg2-sorted", table_name, (1 << 28) * world, "sorted", False)
+            rec["note"] = "BASELINE configs[1] table, points = this rank's slice of linspace(lb, ub) (leaf-uniform fast path)"
+            configs.append(rec)
             # cfg3: 2^30 GLOBAL points over the N GPUs (strong scaling), fp64 order 13
             configs.append(run_config("cfg3", "gen__cfg3_j0_cheb_o13_f64", 1 << CFG3_GLOBAL_LOG2, "uniform", True))
             # cfg4: lookup stress on its own input distribution, both dtypes, 2^28 points per GPU
