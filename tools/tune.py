@@ -39,6 +39,8 @@ VARIANTS = {
     # CTA shape: the same 16 warps per SM as two or four independent CTAs (round 2)
     "blk256_mb2": ["AI_BLOCK=256", "AI_MIN_BLOCKS=2"],
     "blk128_mb4": ["AI_BLOCK=128", "AI_MIN_BLOCKS=4"],
+    # two tiles in flight per thread at the FULL tile size (round 1 only tried it with shrunk tiles)
+    "pf2": ["AI_PREFETCH=2"],
 }
 TABLES = ("approx__32o6-p1.19209289551e-06,approx__32o13-p1.19209289551e-06,gen__cfg3_j0_cheb_o13_f64,"
           "approx__64o7-p2.22044604925e-14,approx__64o6-p1.19209289551e-06,approx__32o3-p1.19209289551e-06")
