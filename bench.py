@@ -551,7 +551,8 @@ def main():
         launches_configs = 0
         b_ref = None
         if do_configs:
-            csteps, cwarm = max(5, min(args.steps, 20)), 3
+            # (10 warm-up launches: after the idle gap the first few launches run below full clocks)
+            csteps, cwarm = max(5, min(args.steps, 20)), 10
 
             def run_config(label, name, n_glob, kind, strong, steps=csteps):
                 """One record: table `name`, n_glob GLOBAL points (this rank takes its contiguous shard)."""
