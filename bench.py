@@ -325,13 +325,16 @@ class Arena(object):
 
     def __init__(self, torch, dev, nbytes):
         self.torch = torch
+        # y starts a few KB off the allocation base so that x and y are not an exact power-of-two
+        # distance apart (experiment hook AI_BENCH_Y_OFFSET, bytes, multiple of 256)
+        self.yoff = int(os.environ.get("AI_BENCH_Y_OFFSET", "0"))
         self.xb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.yb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.yb = torch.empty(nbytes + self.yoff, dtype=torch.uint8, device=dev)
 
     def views(self, np_dtype, n):
         tdt = self.torch.float32 if np_dtype == np.float32 else self.torch.float64
         esz = 4 if np_dtype == np.float32 else 8
-        return self.xb[:n * esz].view(tdt), self.yb[:n * esz].view(tdt)
+        return self.xb[:n * esz].view(tdt), self.yb[self.yoff:self.yoff + n * esz].view(tdt)
 
 
 def main():
@@ -552,7 +555,7 @@ def main():
         b_ref = None
         if do_configs:
             # (10 warm-up launches: after the idle gap the first few launches run below full clocks)
-            csteps, cwarm = max(5, min(args.steps, 20)), 10
+            csteps = max(5, min(args.steps, 20))
 
             def run_config(label, name, n_glob, kind, strong, steps=csteps):
                 """One record: table `name`, n_glob GLOBAL points (this rank takes its contiguous shard)."""
@@ -566,6 +569,9 @@ def main():
                 torch.cuda.synchronize(dev)
                 time.sleep(CONFIG_IDLE_SECONDS)          # every config is a burst like the headline, not the tail of the previous one
                 clocks.mark()
+                # warm-up after the idle gap: the first launches run below full clocks; ten short launches,
+                # three long ones (ten 4 ms launches would already eat into the board's power window)
+                cwarm = 3 if nl * ff.dtype.itemsize >= (1 << 32) else 10
                 tot, kms, kmin = time_table(tt, xx, yy, steps, cwarm)
                 ck = clocks.mark()
                 launches_configs += steps
