@@ -77,6 +77,7 @@ def build(force=False, verbose=False, defines=(), out=None, only=None):
     nvcc = nvcc_path()
     objdir = os.path.join(OBJROOT, "obj_" + out) if variant else OBJDIR
     os.makedirs(objdir, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)         # git-ignored: absent in a fresh checkout
     dflags = ["-D" + d for d in defines]
 
     def compile_one(src):
