@@ -150,6 +150,7 @@ struct ai_table {
     int uniform_hdr = 0;               // 1: records carry no header, computed from the cell (modes kSmemU / kSmemBankU)
     int rank16 = 0;                    // 1: the first[] section holds rank words (view.rank_mode bit 2)
     int compact = 0;                   // 1: kGlobalC image (headerless 32-byte records per coarse cell)
+    int path = 0;                      // 1: path lookup (view.rank_mode bit 4)
     int eval_smem = 0;                 // dynamic shared memory of the eval kernel in this mode
     int aux_smem = 0;                  // ... of the index / sum kernels (packed layouts only)
     std::vector<double> select;        // kSelect: [mid, rec0[kMaxRecord], rec1[kMaxRecord]] (exact widening)
@@ -176,6 +177,14 @@ struct GridPlan {
     int wide_ok = 0;
     unsigned wide_mul = 0, wide_shift = 0;
     std::vector<uint32_t> wide_coarse_leaf;
+    // path lookup (Lookup::path_leaf): replaces grid + search for trees that are a path below level Lc
+    int path_ok = 0;
+    int path_p = 0, path_D = 0, path_Lc = 0;          // scale 2^p; V has D bits; 2^Lc rows
+    long long path_u0 = 0, path_u1 = 0;               // first / last fine cell (absolute)
+    unsigned long long path_mul = 0;                  // 0: q = 1
+    unsigned path_shift = 0;
+    std::vector<unsigned long long> path_target;      // per row
+    std::vector<uint32_t> path_rows;                  // 2^Lc rows of D - Lc + 1 leaf ordinals
 };
 
 long long gcd_ll(long long a, long long b) {
@@ -189,7 +198,7 @@ long long gcd_ll(long long a, long long b) {
 //   * records stored once per coarse cell (coarse_ok): the cell index addresses the record;
 //   * with <= 32 coarse cells, the leaf as the rank of the cell in a bitmap (rank_mode).
 void plan_rank(const std::vector<double>& b, GridPlan* gp) {
-    if (gp->K != 0 || gp->p < 0) return;
+    if (gp->K != 0 || gp->p < 0 || gp->path_ok) return;
     const int64_t L = (int64_t)b.size() - 1;
     const int G = gp->G;
     long long q = 0;
@@ -284,6 +293,138 @@ bool cells_for(const std::vector<double>& b, int p, long long* g0, long long* gl
     return true;
 }
 
+// The PATH lookup (ai_kernels.cuh, Lookup::path_leaf) for tables whose exact grid is far too large
+// (deep bisection towards a discontinuity: BASELINE config 4 has leaf widths from 1.25 down to
+// 10 * 2^-43).  Conditions, all checked here on the exact breakpoints:
+//   * every breakpoint (both ends included) is an integer after scaling by 2^p, p <= 60, and the
+//     fine cell ids stay below 2^31 (fp32) / 2^52 (fp64);
+//   * the domain is W = q * 2^D fine cells wide (q odd) and every breakpoint offset is a multiple of
+//     q, so V = offset / q is a D-bit position; every leaf is a dyadic node of that D-level trie;
+//   * below some level Lc <= 6 every node of the trie is a PATH: at each split at least one child
+//     is a leaf.  Then, with `target` any position inside the deepest leaf of the row's path,
+//     the first bit in which V differs from target names the sibling leaf that holds V.
+// The device formula (multiply-high division included) is then replayed on both sides of every
+// breakpoint; the division is monotone, so that proves it for every fine cell.
+constexpr int kPathMaxRowsLog2 = 6;
+void plan_path(const std::vector<double>& b, int dtype, GridPlan* gp) {
+    if (std::getenv("AI_B200_NO_PATH")) return;
+    const int64_t L = (int64_t)b.size() - 1;
+    if (L < 3 || L > 65535) return;
+    const double lim = (dtype == AI_DTYPE_F32) ? 2147483648.0 : 4503599627370496.0;
+    int p = -1;
+    for (int q = 0; q <= 60 && p < 0; ++q) {
+        bool all = true;
+        for (int64_t k = 0; k <= L && all; ++k) {
+            const double v = std::ldexp(b[k], q);
+            all = (std::fabs(v) < lim) && (v == std::floor(v));
+        }
+        if (all) p = q;
+    }
+    if (p < 0) return;
+    std::vector<long long> off((size_t)L + 1);
+    const long long u0 = (long long)std::ldexp(b[0], p);
+    for (int64_t k = 0; k <= L; ++k) off[(size_t)k] = (long long)std::ldexp(b[k], p) - u0;
+    const long long W = off[(size_t)L];
+    if (W <= 0) return;
+    long long q = W;
+    int D = 0;
+    while ((q & 1) == 0) { q >>= 1; ++D; }
+    const int wordbits = (dtype == AI_DTYPE_F32) ? 32 : 64;
+    if (D < 1 || D >= wordbits - 1) return;
+    std::vector<unsigned long long> V((size_t)L + 1);
+    for (int64_t k = 0; k <= L; ++k) {
+        if (off[(size_t)k] % q) return;
+        V[(size_t)k] = (unsigned long long)(off[(size_t)k] / q);
+    }
+    for (int64_t i = 0; i < L; ++i) {                       // every leaf a dyadic node
+        const unsigned long long w = V[(size_t)i + 1] - V[(size_t)i];
+        if (w == 0 || (w & (w - 1)) || (V[(size_t)i] & (w - 1))) return;
+    }
+    // leaves inside [lo, hi): indices [i0, i1)
+    auto leaf_at = [&](unsigned long long v) {              // leaf holding position v
+        return (int64_t)(std::upper_bound(V.begin(), V.end(), v) - V.begin()) - 1;
+    };
+    auto is_leaf = [&](unsigned long long lo, unsigned long long hi) {   // node [lo, hi) inside ONE leaf?
+        const int64_t i = leaf_at(lo);
+        return V[(size_t)i + 1] >= hi;
+    };
+    for (int Lc = 0; Lc <= std::min(D, kPathMaxRowsLog2); ++Lc) {
+        const int rowlen = D - Lc + 1;
+        const size_t rows = (size_t)1 << Lc;
+        std::vector<unsigned long long> target(rows);
+        std::vector<uint32_t> tab(rows * (size_t)rowlen);
+        bool ok = true;
+        for (size_t r = 0; r < rows && ok; ++r) {
+            unsigned long long lo = (unsigned long long)r << (D - Lc), hi = lo + (1ull << (D - Lc));
+            int level = Lc;                                 // [lo, hi) is the path node of this level
+            uint32_t* row = &tab[r * (size_t)rowlen];
+            while (!is_leaf(lo, hi)) {
+                const unsigned long long mid = lo + ((hi - lo) >> 1);
+                const bool lleaf = is_leaf(lo, mid), rleaf = is_leaf(mid, hi);
+                if (!lleaf && !rleaf) { ok = false; break; }
+                // the path continues into the child that is NOT a leaf (either one if both are);
+                // positions that leave the path at bit `level` sit in the other child
+                if (rleaf) { row[level - Lc] = (uint32_t)leaf_at(mid); hi = mid; }
+                else       { row[level - Lc] = (uint32_t)leaf_at(lo);  lo = mid; }
+                ++level;
+            }
+            if (!ok) break;
+            for (int z = level; z <= D; ++z) row[z - Lc] = (uint32_t)leaf_at(lo);
+            target[r] = lo;
+        }
+        if (!ok) continue;
+        // exact division by q:  floor(u / q) = mulhi(u, M) >> s
+        unsigned long long M = 0;
+        unsigned sh = 0;
+        auto divide = [&](unsigned long long u) -> unsigned long long {
+            if (!M) return u;
+            if (wordbits == 32) return (unsigned long long)((unsigned)(((unsigned long long)(unsigned)u * (unsigned)M) >> 32) >> sh);
+            return (unsigned long long)(((unsigned __int128)u * M) >> 64) >> sh;
+        };
+        auto device_leaf = [&](unsigned long long u) -> int64_t {
+            const unsigned long long v = divide(u);
+            const unsigned long long row = v >> (D - Lc);
+            if (row >= rows) return -1;
+            const unsigned long long x = v ^ target[(size_t)row];
+            int clz = wordbits;
+            if (x) clz = (wordbits == 32) ? __builtin_clz((unsigned)x) : __builtin_clzll(x);
+            const int e = clz - (wordbits - D) - Lc;
+            if (e < 0 || e >= rowlen) return -1;
+            return (int64_t)tab[(size_t)row * rowlen + e];
+        };
+        auto verify = [&]() {
+            for (int64_t k = 0; k < L; ++k) {
+                const unsigned long long a = (unsigned long long)off[(size_t)k], e = (unsigned long long)off[(size_t)k + 1] - 1;
+                if (divide(a) != V[(size_t)k] || divide(e) != V[(size_t)k + 1] - 1) return false;
+                if (device_leaf(a) != k || device_leaf(e) != k) return false;
+                const unsigned long long m = a + ((e - a) >> 1);
+                if (device_leaf(m) != k) return false;
+            }
+            return true;
+        };
+        bool found = (q == 1);
+        if (!found) {
+            for (unsigned s = 0; s < (unsigned)wordbits - 1 && !found; ++s) {
+                const unsigned __int128 one = (unsigned __int128)1 << (wordbits + s);
+                const unsigned __int128 m = (one + (unsigned __int128)q - 1) / (unsigned __int128)q;
+                if (m >> wordbits) break;                   // M must fit the word
+                M = (unsigned long long)m; sh = s;
+                found = verify();
+            }
+            if (!found) { M = 0; sh = 0; }
+        } else {
+            found = verify();
+        }
+        if (!found) return;
+        gp->path_ok = 1; gp->path_p = p; gp->path_D = D; gp->path_Lc = Lc;
+        gp->path_u0 = u0; gp->path_u1 = u0 + W - 1;
+        gp->path_mul = M; gp->path_shift = sh;
+        gp->path_target.swap(target);
+        gp->path_rows.swap(tab);
+        return;
+    }
+}
+
 int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out, int64_t exact_budget_override = 0) {
     const int64_t L = (int64_t)b.size() - 1;
     const long long rep_limit = (dtype == AI_DTYPE_F32) ? (1LL << 24) : (1LL << 30);
@@ -369,6 +510,13 @@ int plan_grid(const std::vector<double>& b, int dtype, GridPlan* out, int64_t ex
     }
     out->p = p; out->G = (int)(gl - g0 + 1); out->g0 = g0;
     out->K = K;
+    // a search would follow: the path lookup instead, when the tree is a path below some level
+    if (!exact && K > 0) plan_path(b, dtype, out);
+    if (out->path_ok) {
+        out->p = out->path_p; out->G = 1 << out->path_Lc; out->g0 = out->path_u0;
+        out->K = 0;
+        out->first.clear();
+    }
     if (!std::getenv("AI_B200_NO_RANK")) plan_rank(b, out);     // (env: test hook for the table path)
     return AI_OK;
 }
@@ -502,11 +650,31 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
     const bool rank16 = !gp.rank16.empty() && !cell_records && gp.K == 0 && !gp.rank_mode
                         && (size_t)gp.G * (size_t)(4 >> fshift) > rank16_min;
     if (rank16) fshift = 3;
-    const int off_breaks = rank16 ? round_up16(gp.rank16.size() * 4) : round_up16((size_t)gp.G * (size_t)(4 >> fshift));
+    // path lookup: first[] = one target word per row (32-bit for float, 64-bit for double), then the
+    // rows of leaf ordinals (bytes up to 256 leaves, else 16-bit)
+    const bool path = gp.path_ok != 0;
+    const int path_toff = path ? round_up16(gp.path_target.size() * sizeof(T)) : 0;
+    const bool path_t16 = L > 256;
+    const int off_breaks = path ? path_toff + round_up16(gp.path_rows.size() * (path_t16 ? 2 : 1))
+                         : rank16 ? round_up16(gp.rank16.size() * 4) : round_up16((size_t)gp.G * (size_t)(4 >> fshift));
     const int off_records = off_breaks + round_up16((size_t)(L + 1 + pad) * sizeof(T));
     const size_t total = (size_t)off_records + (size_t)round_up16((size_t)NR * R * sizeof(T));
     image->assign(total, 0);
-    if (rank16) {
+    if (path) {
+        for (size_t r = 0; r < gp.path_target.size(); ++r) {
+            if constexpr (sizeof(T) == 4) {
+                const uint32_t w = (uint32_t)gp.path_target[r];
+                std::memcpy(image->data() + off_first + 4 * r, &w, 4);
+            } else {
+                std::memcpy(image->data() + off_first + 8 * r, &gp.path_target[r], 8);
+            }
+        }
+        unsigned char* rows = image->data() + off_first + path_toff;
+        for (size_t e = 0; e < gp.path_rows.size(); ++e) {
+            if (path_t16) { const uint16_t w = (uint16_t)gp.path_rows[e]; std::memcpy(rows + 2 * e, &w, 2); }
+            else rows[e] = (unsigned char)gp.path_rows[e];
+        }
+    } else if (rank16) {
         std::memcpy(image->data() + off_first, gp.rank16.data(), gp.rank16.size() * sizeof(uint32_t));
     } else if (fshift == 2) {
         for (int g = 0; g < gp.G; ++g) (*image)[off_first + g] = (unsigned char)gp.first[g];
@@ -517,6 +685,9 @@ int build_image(ai_table* t, const GridPlan& gp, bool global_layout, std::vector
         std::memcpy(image->data() + off_first, gp.first.data(), gp.first.size() * sizeof(uint32_t));
     }
     t->view.first_shift = fshift;
+    t->path = path ? 1 : 0;
+    t->view.path_toff = path_toff;
+    t->view.path_t16 = path_t16 ? 1 : 0;
     T* br = reinterpret_cast<T*>(image->data() + off_breaks);
     for (int64_t k = 0; k <= L; ++k) br[k] = (T)t->breaks[k];
     for (int k = 0; k < pad; ++k) br[L + 1 + k] = std::numeric_limits<T>::infinity();
@@ -634,7 +805,7 @@ bool build_compact_image(ai_table* t, const GridPlan& gp, std::vector<unsigned c
         for (int j = 0; j <= n; ++j) rec[c * R + j] = (T)t->coef[(size_t)i * (n + 1) + j];
     }
     t->rstride = R;
-    t->packed = 0; t->uniform_hdr = 0; t->rank16 = 0;
+    t->packed = 0; t->uniform_hdr = 0; t->rank16 = 0; t->path = 0;
     t->cell_records = 1;
     t->compact = 1;
     t->view.first_shift = fshift;
@@ -663,14 +834,14 @@ bool build_compact_image(ai_table* t, const GridPlan& gp, std::vector<unsigned c
 // what build_image / build_compact_image write into the table, to put it back when a layout is
 // built but not taken
 struct SavedPlan {
-    int rstride, packed, uniform_hdr, rank16, cell_records, compact;
+    int rstride, packed, uniform_hdr, rank16, cell_records, compact, path;
     ai::TableView view;
     explicit SavedPlan(const ai_table* t)
         : rstride(t->rstride), packed(t->packed), uniform_hdr(t->uniform_hdr), rank16(t->rank16),
-          cell_records(t->cell_records), compact(t->compact), view(t->view) {}
+          cell_records(t->cell_records), compact(t->compact), path(t->path), view(t->view) {}
     void restore(ai_table* t) const {
         t->rstride = rstride; t->packed = packed; t->uniform_hdr = uniform_hdr; t->rank16 = rank16;
-        t->cell_records = cell_records; t->compact = compact; t->view = view;
+        t->cell_records = cell_records; t->compact = compact; t->path = path; t->view = view;
     }
 };
 
@@ -913,7 +1084,16 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->view.n_leaves = (int)L;
     t->view.g0 = (int)gp.g0;
     t->view.kstep = gp.K > 0 ? (1 << (gp.K - 1)) : 0;
-    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0) | (t->rank16 ? 4 : 0) | (compact ? 8 : 0);
+    t->view.rank_mode = (gp.rank_mode ? 1 : 0) | (t->cell_records ? 2 : 0) | (t->rank16 ? 4 : 0) | (compact ? 8 : 0)
+                        | (t->path ? 16 : 0);
+    if (t->path) {
+        const int wordbits = (t->dtype == AI_DTYPE_F32) ? 32 : 64;
+        t->view.path_mul = gp.path_mul;
+        t->view.path_shift = gp.path_shift;
+        t->view.path_cshift = (unsigned)(gp.path_D - gp.path_Lc);
+        t->view.path_rowlen = gp.path_D - gp.path_Lc + 1;
+        t->view.path_zbias = (wordbits - gp.path_D) + gp.path_Lc;
+    }
     t->view.div_mul = gp.div_mul;
     t->view.div_shift = gp.div_shift;
     t->view.div_add = gp.div_add;
@@ -922,6 +1102,10 @@ int plan_table(ai_table* t, size_t smem_cap, std::vector<unsigned char>* image_o
     t->view.scale = std::ldexp(1.0, gp.p);
     t->view.lo = (double)gp.g0;
     t->view.hi = (double)(gp.g0 + gp.G - 1);
+    if (t->path) {                       // the fine cells of the path lookup (not the row count G)
+        t->view.hi = (double)gp.path_u1;
+        t->view.g0 = (t->dtype == AI_DTYPE_F32) ? (int)gp.path_u0 : 0;
+    }
     // adapt.py:107 `*(1./n)`: 1./n in double, then rounded to the table dtype by the multiply
     const double inv = t->order > 0 ? 1.0 / (double)t->order : 0.0;
     t->view.inv_order = (t->dtype == AI_DTYPE_F32) ? (double)(float)inv : inv;
@@ -1558,7 +1742,7 @@ int ai_table_get_info(const ai_table_t* t, ai_table_info_t* info) {
     info->cell_records = t->cell_records;
     info->bank_copies = (t->mode == ai::kSmemVC) ? ai::kVecCopies : t->copies;
     info->smem_resident = t->smem_resident;
-    info->lookup_mode = t->rank_mode ? 2 : (t->K > 0 ? 1 : (t->rank16 ? 3 : 0));
+    info->lookup_mode = t->path ? 4 : (t->rank_mode ? 2 : (t->K > 0 ? 1 : (t->rank16 ? 3 : 0)));
     info->block_threads = ai::kBlock; info->blocks_per_sm = t->blocks_per_sm; info->sm_count = t->sm_count;
     info->lower_bound = t->breaks.front(); info->upper_bound = t->breaks.back();
     return AI_OK;

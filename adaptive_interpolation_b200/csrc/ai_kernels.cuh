@@ -174,6 +174,15 @@ struct TableView {
                                    // (kGlobalC: u_w = coarse cell width, s0_hi / s0_lo = bits of S1 = 2 / u_w)
     int off_aux, aux_bytes;        // kGlobalC: 4-bit level per coarse cell (two per byte), staged in shared memory
     unsigned wide_mul, wide_shift; // kGlobalC: coarse cell = ((fine cell - g0) * wide_mul) >> wide_shift, 64-bit product
+    // rank_mode bit 4, the PATH lookup of deep skewed trees (Lookup::path_leaf): first[] holds one
+    // target word per row followed by the rows of leaf ordinals
+    unsigned long long path_mul;   // floor(u / q) = mulhi(u, path_mul) >> path_shift; 0: q = 1
+    unsigned path_shift;
+    unsigned path_cshift;          // row = V >> path_cshift
+    int path_rowlen;               // entries per row
+    int path_zbias;                // entry = row * path_rowlen + clz(V ^ target[row]) - path_zbias
+    int path_toff;                 // byte offset of the rows inside first[]
+    int path_t16;                  // rows hold 16-bit leaf ordinals (more than 256 leaves), else bytes
 };
 
 // ---------------------------------------------------------------------------------- helpers
@@ -237,6 +246,10 @@ template <typename T> struct Lookup {
     int fshift, rank_mode;
     unsigned div_mul, div_shift, div_add, cont;
     unsigned wide_mul, wide_shift;
+    unsigned long long path_mul;
+    unsigned path_shift, path_cshift;
+    int path_rowlen, path_zbias, path_t16;
+    const unsigned char* path_rows;
     const unsigned char* first;    // packed 8-bit (L <= 256) or 16-bit entries
     const unsigned char* bbase;    // breaks[] base (uniform); element j of this lane lives at
     int bunit_log2;                //   bbase + (j << bunit_log2) + blane
@@ -248,6 +261,9 @@ template <typename T> struct Lookup {
         fshift = tv.first_shift; rank_mode = tv.rank_mode; nbreaks = tv.n_breaks_elems;
         div_mul = tv.div_mul; div_shift = tv.div_shift; div_add = tv.div_add; cont = tv.cont_mask;
         wide_mul = tv.wide_mul; wide_shift = tv.wide_shift;
+        path_mul = tv.path_mul; path_shift = tv.path_shift; path_cshift = tv.path_cshift;
+        path_rowlen = tv.path_rowlen; path_zbias = tv.path_zbias; path_t16 = tv.path_t16;
+        path_rows = base + tv.off_first + tv.path_toff;
         first = base + tv.off_first;
         bbase = base + tv.off_breaks;
         bunit_log2 = (sizeof(T) == 4) ? 2 : 3;
@@ -312,6 +328,38 @@ template <typename T> struct Lookup {
         AI_CHECK(i >= 0 && i <= lmax);
         return i;
     }
+    // Deep skewed trees (BASELINE config 4: bisection towards a discontinuity, depth 43): the exact
+    // grid would need 2^45 cells and a coarser grid leaves a K-step search (K dependent loads of a
+    // breakpoint, each with a compare and a select).  Such a tree is a PATH below some level Lc:
+    // every split has one child that is a leaf.  With V = the point's position in units of the
+    // narrowest leaf (floor(x * 2^p) is exact; the odd factor q of the domain width divides out by
+    // an exact multiply-high), the leaf is decided by the first bit in which V leaves the path,
+    // i.e. by clz(V ^ target) -- one load of the row's target word and one of the leaf ordinal,
+    // whatever the depth.  The host checks the formula on both sides of every breakpoint.
+    template <bool DIV>
+    __device__ __forceinline__ int path_leaf(T x) const {
+        int e;
+        if constexpr (sizeof(T) == 4) {
+            unsigned v = cell_abs(x) - (unsigned)g0;
+            if constexpr (DIV) v = __umulhi(v, (unsigned)path_mul) >> path_shift;
+            const unsigned row = v >> path_cshift;
+            const unsigned tgt = reinterpret_cast<const unsigned*>(first)[row];
+            e = (int)row * path_rowlen + __clz((int)(v ^ tgt)) - path_zbias;
+        } else {
+            // clamp as a double (lo, hi and every cell id are exact below 2^52; NaN -> lo)
+            const double u = fmin(fmax(floor(x * scale), lo), hi) - lo;
+            unsigned long long v = (unsigned long long)__double2ll_rz(u);
+            if constexpr (DIV) v = __umul64hi(v, path_mul) >> path_shift;
+            const unsigned row = (unsigned)(v >> path_cshift);
+            const unsigned long long tgt = reinterpret_cast<const unsigned long long*>(first)[row];
+            e = (int)row * path_rowlen + __clzll((long long)(v ^ tgt)) - path_zbias;
+        }
+        AI_CHECK(e >= 0);
+        const int i = path_t16 ? (int)reinterpret_cast<const unsigned short*>(path_rows)[e]
+                               : (int)path_rows[e];
+        AI_CHECK(i >= 0 && i <= lmax);
+        return i;
+    }
     // RECORD index of N points held in registers: the leaf ordinal, except for tables whose
     // records are stored once per coarse cell (rank_mode 2: at most 32 / 16 cells), where the
     // coarse cell itself addresses the record and the rank (shift, mask, popc, subtract) is not
@@ -329,6 +377,16 @@ template <typename T> struct Lookup {
     // the LEAF ordinal (what the index kernel reports), whatever the record layout
     template <int N>
     __device__ __forceinline__ void true_leaves(const T (&x)[N], int (&i)[N]) const {
+        if (rank_mode & 16) {
+            if (path_mul) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) i[e] = path_leaf<true>(x[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < N; ++e) i[e] = path_leaf<false>(x[e]);
+            }
+            return;
+        }
         if (rank_mode & 1) {
 #pragma unroll
             for (int e = 0; e < N; ++e) i[e] = rank_guess(x[e]);

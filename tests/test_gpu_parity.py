@@ -135,6 +135,7 @@ def test_index_adversarial_neighbourhoods(name):
 def test_index_exact_in_forced_search_mode(name, cells, monkeypatch):
     """Cap the grid so that the bounded binary search does the work on every table."""
     monkeypatch.setenv("AI_B200_MAX_CELLS", str(cells))
+    monkeypatch.setenv("AI_B200_NO_PATH", "1")
     g = golden(name)
     tab = dev_table(name)
     info = tab.info()
@@ -144,8 +145,50 @@ def test_index_exact_in_forced_search_mode(name, cells, monkeypatch):
     assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
     y = gpu_eval(tab, g.x)
     monkeypatch.delenv("AI_B200_MAX_CELLS")
+    monkeypatch.delenv("AI_B200_NO_PATH")
     y0 = gpu_eval(dev_table(name), g.x)
     assert np.array_equal(y, y0, equal_nan=True)                  # same leaf -> same arithmetic
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_index_exact_with_the_path_lookup(name, monkeypatch):
+    """Deep skewed trees (config 4) find the leaf from clz(position ^ path target): one row word and
+    one leaf ordinal instead of a K-step search.  Cap the grid at two cells so that every table whose
+    tree is a path below level 6 takes it (94 of the 116 golden tables), and require the reference's
+    indices on the golden points, on every breakpoint and its neighbours, and out of the domain."""
+    g = golden(name)
+    f = tables.flatten(g)
+    natural = dev_table(name).info()["lookup_mode"] == 4           # the two config-4 tables
+    if not natural:
+        monkeypatch.setenv("AI_B200_MAX_CELLS", "2")
+    tab = dev_table(name)
+    info = tab.info()
+    if info["lookup_mode"] != 4:
+        pytest.skip("not a path below level 6")
+    assert info["search_steps"] == 0 and info["grid_cells"] <= 64
+    assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
+    dt = g.dtype
+    pts = [f.breaks]
+    lo, hi = f.breaks.copy(), f.breaks.copy()
+    for _ in range(4):
+        lo, hi = np.nextafter(lo, dt(-np.inf)), np.nextafter(hi, dt(np.inf))
+        pts += [lo.copy(), hi.copy()]
+    tiny = np.finfo(dt).tiny
+    pts.append(np.array([np.inf, -np.inf, np.nan, 0.0, -0.0, tiny, -tiny, np.finfo(dt).max, -np.finfo(dt).max,
+                         1e30, -1e30], dtype=dt))
+    span = float(f.breaks[-1]) - float(f.breaks[0])
+    pts.append(np.random.default_rng(5).uniform(float(f.breaks[0]) - 0.05 * span, float(f.breaks[-1]) + 0.05 * span,
+                                                1 << 16).astype(dt))
+    x = np.concatenate(pts).astype(dt)
+    assert np.array_equal(gpu_index(tab, x), oracle_np.leaf_index(f.breaks, x))
+    y = gpu_eval(tab, g.x)
+    if not natural:
+        monkeypatch.delenv("AI_B200_MAX_CELLS")
+    else:
+        monkeypatch.setenv("AI_B200_NO_PATH", "1")                 # against grid + search
+    tab0 = dev_table(name)
+    assert tab0.info()["lookup_mode"] != 4
+    assert np.array_equal(y, gpu_eval(tab0, g.x), equal_nan=True)  # same leaf -> same arithmetic
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -392,6 +435,19 @@ def _random_breaks(rng, dtype, kind):
     elif kind == "uniform":                  # equal leaves (computed header), dyadic or not
         lo = float(rng.integers(-8, 8))
         b = lo + float(rng.choice([1.0, 20.0, 0.625, 3.0, 0.1])) * np.arange(L + 1) / float(rng.choice([1, 4, 16, L]))
+    elif kind == "path":                     # bisection towards a few points: deep, skewed, dyadic (config 4)
+        lo = float(rng.integers(-50, 50))
+        width = float(rng.choice([1.0, 10.0, 20.0, 0.375, 6.0]))
+        depth = 22 if dtype == np.float32 and abs(lo) + width > 16 else (18 if dtype == np.float32 else 44)
+        targets = rng.uniform(0, 1, int(rng.integers(1, 5)))
+        cuts = {0.0, 1.0}
+        for t in targets:
+            a, c = 0.0, 1.0
+            for _ in range(int(rng.integers(3, depth))):
+                m = (a + c) / 2
+                cuts.add(m)
+                a, c = (m, c) if t >= m else (a, m)
+        b = lo + width * np.array(sorted(cuts))
     elif kind == "clustered":                # geometric clustering around a point (config 4 style)
         c = rng.uniform(-5, 5)
         off = np.concatenate([-(2.0 ** -np.arange(1, L // 2 + 2)), 2.0 ** -np.arange(1, L // 2 + 2)])
@@ -402,14 +458,14 @@ def _random_breaks(rng, dtype, kind):
     return b if len(b) >= 2 else np.array([0, 1], dtype=dtype)
 
 
-@pytest.mark.parametrize("kind", ["dyadic", "random", "huge", "tiny", "clustered", "uniform"])
+@pytest.mark.parametrize("kind", ["dyadic", "random", "huge", "tiny", "clustered", "uniform", "path"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_lookup_exact_on_random_tables(kind, dtype):
     """Property test of the grid planner + device lookup: for arbitrary sorted breakpoints the
     leaf index equals the closed form of the reference's BST walk, on every breakpoint, its
     neighbours and random points, in whichever lookup / residency mode the library picks."""
     # deterministic by default; AI_TEST_SEED=<n> explores other tables (tools/gpu_round_check.sh runs a few)
-    kinds = ["dyadic", "random", "huge", "tiny", "clustered", "uniform"]
+    kinds = ["dyadic", "random", "huge", "tiny", "clustered", "uniform", "path"]
     rng = np.random.default_rng([kinds.index(kind), np.dtype(dtype).itemsize, int(os.environ.get("AI_TEST_SEED", "0"))])
     seen, seen_shapes = set(), set()
     for trial in range(16):
@@ -446,6 +502,8 @@ def test_lookup_exact_on_random_tables(kind, dtype):
         seen_shapes.add((basis, order))
     report(test="random_tables", kind=kind, dtype=np.dtype(dtype).name, modes=sorted(map(list, seen)),
            shapes=sorted(map(list, seen_shapes)))
+    if kind == "path":
+        assert any(m[0] == 4 for m in seen), seen                  # the path lookup was exercised
 
 
 def test_residency_selection():
@@ -472,7 +530,7 @@ def test_lookup_modes_of_saved_tables():
     # BASELINE config 2's table (15 leaves, 16 coarse cells) must take the register-only path
     assert modes["approx__32o6-p1.19209289551e-06"] == 2
     assert modes["gen__cfg3_j0_cheb_o13_f64"] == 2
-    assert modes["gen__cfg4_f1_leg_o7_f64"] == 1
+    assert modes["gen__cfg4_f1_leg_o7_f64"] == 4 and modes["gen__cfg4_f1_leg_o7_f32"] == 4   # path lookup
 
 
 def test_saved_tables_need_no_search():

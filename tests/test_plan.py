@@ -72,10 +72,19 @@ def test_saved_tables_plan():
 def test_config_tables_plan():
     cfg3 = plan("gen__cfg3_j0_cheb_o13_f64")
     assert cfg3["lookup_mode"] == 2 and cfg3["header_packed"] == 2 and cfg3["residency"] == 0   # 8 equal leaves
-    for name, k, res in (("gen__cfg4_f1_leg_o7_f32", 4, 1), ("gen__cfg4_f1_leg_o7_f64", 6, 9)):
-        info = plan(name)                               # deep skewed trees: grid + bounded search
-        assert info["search_steps"] == k and info["lookup_mode"] == 1 and info["header_packed"] == 0
+    for name, p, res in (("gen__cfg4_f1_leg_o7_f32", 20, 1), ("gen__cfg4_f1_leg_o7_f64", 42, 9)):
+        info = plan(name)                               # deep skewed trees (depth 21 / 43): the path lookup,
+        assert info["lookup_mode"] == 4 and info["search_steps"] == 0           # 8 rows below level 3
+        assert info["grid_cells"] == 8 and info["grid_log2_scale"] == p and info["header_packed"] == 0
         assert info["residency"] == res                 # fp32: per-bank copies fit; fp64: 8 x 128-bit
+
+
+def test_config4_tables_without_the_path_lookup(monkeypatch):
+    monkeypatch.setenv("AI_B200_NO_PATH", "1")
+    for name, k, res in (("gen__cfg4_f1_leg_o7_f32", 4, 1), ("gen__cfg4_f1_leg_o7_f64", 6, 9)):
+        info = plan(name)                               # grid + bounded search
+        assert info["search_steps"] == k and info["lookup_mode"] == 1 and info["header_packed"] == 0
+        assert info["residency"] == res and info["grid_cells"] == 80
 
 
 def test_smaller_shared_memory_changes_the_residency(monkeypatch):
@@ -98,9 +107,13 @@ def test_hooks(monkeypatch):
     monkeypatch.setenv("AI_B200_NO_RANK", "1")
     assert plan(name)["lookup_mode"] == 0
     monkeypatch.delenv("AI_B200_NO_RANK")
-    monkeypatch.setenv("AI_B200_MAX_CELLS", "8")                                 # grid too coarse: search follows
+    monkeypatch.setenv("AI_B200_MAX_CELLS", "8")                                 # grid too coarse: the tree is a path
+    info = plan(name)                                                            # below level 4 (16 rows)
+    assert info["lookup_mode"] == 4 and info["search_steps"] == 0 and info["grid_cells"] <= 64
+    monkeypatch.setenv("AI_B200_NO_PATH", "1")                                   # ... or a search follows
     info = plan(name)
     assert info["grid_cells"] <= 8 and info["search_steps"] >= 1 and info["lookup_mode"] == 1
+    monkeypatch.delenv("AI_B200_NO_PATH")
     monkeypatch.delenv("AI_B200_MAX_CELLS")
     for mode in (0, 1, 2, 9, 10, 11):
         monkeypatch.setenv("AI_B200_FORCE_MODE", str(mode))
@@ -152,6 +165,19 @@ def _random_breaks(rng, dtype, kind):
             if c[k + 1] - c[k] > 2.0 ** -18:
                 cuts.add((c[k] + c[k + 1]) / 2)
         b = lo + width * np.array(sorted(cuts))
+    elif kind == "path":                     # bisection towards a few points (config 4 style): deep and skewed
+        lo = float(rng.integers(-50, 50))
+        width = float(rng.choice([1.0, 10.0, 20.0, 0.375, 6.0]))
+        depth = 22 if dtype == np.float32 and abs(lo) + width > 16 else (18 if dtype == np.float32 else 44)
+        targets = rng.uniform(0, 1, int(rng.integers(1, 5)))
+        cuts = {0.0, 1.0}
+        for t in targets:
+            a, c = 0.0, 1.0
+            for _ in range(int(rng.integers(3, depth))):
+                m = (a + c) / 2
+                cuts.add(m)
+                a, c = (m, c) if t >= m else (a, m)
+        b = lo + width * np.array(sorted(cuts))
     elif kind == "uniform":
         b = np.linspace(float(rng.integers(-5, 5)), float(rng.integers(6, 40)), L + 1)
     else:
@@ -164,11 +190,11 @@ def _random_breaks(rng, dtype, kind):
 SEED = 0
 
 
-@pytest.mark.parametrize("kind", ["dyadic", "uniform", "random"])
+@pytest.mark.parametrize("kind", ["dyadic", "uniform", "random", "path"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_planner_invariants_on_random_tables(kind, dtype):
     """Whatever the breakpoints, the plan fits the device and its flags are consistent."""
-    rng = np.random.default_rng([["dyadic", "uniform", "random"].index(kind), np.dtype(dtype).itemsize, SEED])
+    rng = np.random.default_rng([["dyadic", "uniform", "random", "path"].index(kind), np.dtype(dtype).itemsize, SEED])
     seen = set()
     for _ in range(60):
         b = _random_breaks(rng, dtype, kind)
@@ -192,6 +218,11 @@ def test_planner_invariants_on_random_tables(kind, dtype):
             assert info["smem_bytes"] == 0 and info["smem_resident"] == 0
         if info["search_steps"] > 0:                                 # breakpoints off the grid
             assert info["lookup_mode"] == 1 and info["header_packed"] != 2 and not info["cell_records"]
+        if info["lookup_mode"] == 4:                                 # path lookup: at most 64 rows, nothing else
+            assert info["search_steps"] == 0 and info["grid_cells"] <= 64 and not info["cell_records"]
+            assert info["header_packed"] != 2 and info["residency"] in (0, 1, 2, 3, 9)
+    if kind == "path":
+        assert any(m[1] == 4 for m in seen), seen
     assert len(seen) >= 2
 
 
