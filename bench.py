@@ -581,7 +581,8 @@ def main():
                 rec = {"config": label, "workload": name, "points": n_glob, "points_per_gpu": nl,
                        "point_distribution": kind, "scaling": "strong" if strong else "weak",
                        "dtype": f_dt, "basis": ff.basis, "order": ff.order,
-                       "leaves": ff.n_leaves, "search_steps": ti["search_steps"], "residency": ti["residency"],
+                       "leaves": ff.n_leaves, "search_steps": ti["search_steps"], "lookup_mode": ti["lookup_mode"],
+                       "residency": ti["residency"],
                        "value": n_glob * steps / (tot * 1e-3) / 1e9, "unit": UNIT, "steps": steps,
                        "kernel_ms": kms_max, "kernel_ms_min": kmin,
                        "frac": frac_of_hbm(nl, ff.dtype.itemsize, kms_max),

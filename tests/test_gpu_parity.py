@@ -199,7 +199,7 @@ def test_table_lookup_path_when_rank_mode_disabled(name, monkeypatch):
     tab_default = dev_table(name)
     monkeypatch.setenv("AI_B200_NO_RANK", "1")
     tab = dev_table(name)
-    assert tab.info()["lookup_mode"] in (0, 1)
+    assert tab.info()["lookup_mode"] in (0, 1, 4)                  # (4: the config-4 tables' path lookup)
     assert np.array_equal(gpu_index(tab, g.x), g.idx_ref)
     assert np.array_equal(gpu_eval(tab, g.x), gpu_eval(tab_default, g.x), equal_nan=True)
 
@@ -539,8 +539,9 @@ def test_saved_tables_need_no_search():
         info = dev_table(name).info()
         assert info["search_steps"] == 0 and info["smem_resident"] == 1, (name, info)
         assert info["image_bytes"] <= 48 * 1024 and info["residency"] in (0, 1, 3, 4, 9, 11)
-    for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
-        assert dev_table(name).info()["search_steps"] >= 1
+    for name in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):      # too deep for a grid: path lookup
+        info = dev_table(name).info()
+        assert info["search_steps"] == 0 and info["lookup_mode"] == 4
 
 
 # ------------------------------------------------------------------ larger seeded inputs vs oracle
