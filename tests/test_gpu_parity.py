@@ -412,6 +412,59 @@ def test_tables_around_the_shared_memory_capacity(order, dtype):
     assert len(seen) >= 3, seen
 
 
+def _path_breaks(lo, width, targets, depth, dtype):
+    """Bisection of [lo, lo + width] towards each target (fractions of the width) down to `depth` levels."""
+    cuts = {0.0, 1.0}
+    for t in targets:
+        a, c = 0.0, 1.0
+        for _ in range(depth):
+            m = (a + c) / 2
+            cuts.add(m)
+            a, c = (m, c) if t >= m else (a, m)
+    return (lo + width * np.array(sorted(cuts))).astype(dtype)
+
+
+@pytest.mark.parametrize("lo,width,ntarget,depth,dtype,basis", [
+    (0.0, 10.0, 8, 43, np.float64, "legendre"),      # 330+ leaves: 16-bit row entries; odd factor 5
+    (-3.0, 8.0, 8, 44, np.float64, "chebyshev"),     # power-of-two width: no division; negative lower bound
+    (1.0, 6.0, 3, 50, np.float64, "monomial"),       # odd factor 3, positions of 50 bits
+    (0.0, 10.0, 5, 20, np.float32, "legendre"),      # config 4's shape in fp32
+    (-2.0, 4.0, 8, 21, np.float32, "chebyshev"),     # no division, 32-bit positions, negative lower bound
+    (40.0, 24.0, 2, 18, np.float32, "chebyshev"),    # domain far from zero, odd factor 3
+])
+def test_path_lookup_on_constructed_trees(lo, width, ntarget, depth, dtype, basis):
+    """Trees bisected towards a few points (what the reference's fitter builds around discontinuities):
+    the path lookup must be chosen and give the oracle's leaf on every breakpoint, its neighbours,
+    points clustered at 2^-j around the targets, and out-of-domain / special values."""
+    targets = (np.arange(ntarget) + 0.3) / ntarget
+    b = _path_breaks(lo, width, targets, depth, dtype)
+    L = len(b) - 1
+    order = 5
+    coef = np.random.default_rng(L).standard_normal((L, order + 1)).astype(dtype)
+    tab = tables.DeviceTable(tables.FlatTable(basis, order, dtype, b, coef), 0)
+    info = tab.info()
+    assert info["lookup_mode"] == 4 and info["search_steps"] == 0, info
+    rng = np.random.default_rng(11)
+    inf = dtype(np.inf)
+    near = (lo + width * targets)[None, :] + (rng.choice([-1.0, 1.0], (4096, 1)) * np.abs(rng.standard_normal((4096, 1)))
+                                              * width * 2.0 ** -rng.integers(1, depth + 6, (4096, 1)))
+    x = np.concatenate([b, np.nextafter(b, -inf), np.nextafter(b, inf), near.ravel().astype(dtype),
+                        rng.uniform(lo - 0.1 * width, lo + 1.1 * width, 1 << 16).astype(dtype),
+                        np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, np.finfo(dtype).tiny, np.finfo(dtype).max,
+                                  -np.finfo(dtype).max], dtype=dtype)])
+    want = oracle_np.leaf_index(b, x)
+    got = gpu_index(tab, x)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (info, x[bad[:5]], got[bad[:5]], want[bad[:5]])
+    xin = x[np.isfinite(x) & (x >= b[0]) & (x < b[-1])]
+    y = gpu_eval(tab, xin)
+    y_o = oracle_np.evaluate(b, coef, basis, order, xin)
+    scale = oracle_np.error_scale(b, coef, basis, order, xin)
+    ok = np.isfinite(scale)
+    assert np.all(np.abs(y[ok].astype(np.float64) - y_o[ok]) <= value_tolerance(dtype, scale[ok], GPU_ULPS)), info
+    report(test="path_constructed", leaves=L, dtype=np.dtype(dtype).name, rows=info["grid_cells"], residency=info["residency"])
+
+
 def _random_breaks(rng, dtype, kind):
     """Sorted, strictly increasing breakpoints of assorted nastiness."""
     L = int(rng.integers(1, 300))
