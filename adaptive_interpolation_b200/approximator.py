@@ -104,9 +104,16 @@ class _Unpickler(pickle.Unpickler):
                 return pickle.Unpickler.find_class(self, module, name)     # the reference's own class
             except (ImportError, AttributeError):
                 return _STANDINS[(module, name)]
-        if module.startswith("numpy.core"):
-            # numpy >= 2 moved numpy.core -> numpy._core (the old name only warns)
-            module = module.replace("numpy.core", "numpy._core", 1)
+        if module.startswith("numpy.core") or module.startswith("numpy._core"):
+            # numpy >= 2 moved numpy.core -> numpy._core; the saved pickles name numpy.core.  Try the
+            # spelling this numpy prefers first and the other one on failure (numpy 1.x has no _core).
+            new = module.replace("numpy.core", "numpy._core", 1)
+            old = module.replace("numpy._core", "numpy.core", 1)
+            first, second = (new, old) if int(np.__version__.split(".")[0]) >= 2 else (old, new)
+            try:
+                return pickle.Unpickler.find_class(self, first, name)
+            except (ImportError, AttributeError):
+                return pickle.Unpickler.find_class(self, second, name)
         return pickle.Unpickler.find_class(self, module, name)
 
 
