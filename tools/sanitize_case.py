@@ -42,7 +42,8 @@ def child():
         y0, y1 = torch.empty_like(xd), torch.empty_like(xd)
         tables.DeviceTable.eval_multi_ptr([tab, tab], xd.data_ptr(), [y0.data_ptr(), y1.data_ptr()], xd.numel(), None)
         torch.cuda.synchronize()
-        print(name, "mode", os.environ.get("AI_B200_FORCE_MODE", "auto"), "residency", info["residency"],
+        print(name, "mode", os.environ.get("AI_B200_FORCE_MODE", "auto"), "cells", os.environ.get("AI_B200_MAX_CELLS", "-"),
+              "residency", info["residency"],
               "lookup", info["lookup_mode"], "ok", flush=True)
 
 
@@ -50,7 +51,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for mode in (None, "0", "1", "2", "3", "4", "9", "10", "nohdr", "nocell", "norank"):
+        for mode in (None, "0", "1", "2", "3", "4", "9", "10", "nohdr", "nocell", "norank", "path", "nopath"):
             env = dict(os.environ)
             if mode == "nohdr":
                 env["AI_B200_NO_PACKED_HDR"] = env["AI_B200_NO_UNIFORM_HDR"] = "1"
@@ -58,6 +59,11 @@ if __name__ == "__main__":
                 env["AI_B200_NO_CELL_RECORDS"] = env["AI_B200_NO_UNIFORM_HDR"] = "1"
             elif mode == "norank":
                 env["AI_B200_NO_RANK"] = "1"
+            elif mode == "path":             # grid capped at two cells: every tree that is a path takes the path lookup
+                env["AI_B200_MAX_CELLS"] = "2"
+            elif mode == "nopath":           # ... and the bounded search otherwise
+                env["AI_B200_MAX_CELLS"] = "2"
+                env["AI_B200_NO_PATH"] = "1"
             elif mode is not None:
                 env["AI_B200_FORCE_MODE"] = mode
             r = subprocess.run([sys.executable, __file__, "child"], env=env)
