@@ -1258,6 +1258,14 @@ eval_multi_kernel(const __grid_constant__ MultiArgs args, const T* __restrict__ 
 }
 
 // The reference's no-"output" variant (generate.py:284,392-394): reduce y instead of storing it.
+// Same tile structure as eval_kernel -- 128-bit streaming loads, the next tile's x in flight while
+// the current one is evaluated, lookups of a whole tile before its gathers, packed FP32, the
+// leaf-uniform fast path -- with the store replaced by an fp64 accumulation per thread (every value
+// is widened before it is added: the header's contract).  x needs no particular alignment: the
+// kernel splits [0, n) into a scalar head up to the first 16-byte boundary, vectors and a tail.
+// Reads 1 * sizeof(T) bytes per point, so at the rate of eval_kernel it is SM-bound, not HBM-bound.
+// (Round 2, first version: one point per thread per iteration, a single load in flight per thread:
+// 124-136 Gpt/s whatever the table, i.e. slower than evaluating AND storing.)
 template <int BASIS, int ORDER, typename T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict__ result, long long n) {
@@ -1271,28 +1279,136 @@ eval_sum_kernel(const TableView tv, const T* __restrict__ x, double* __restrict_
     constexpr int R = rec_stride_for<BASIS, ORDER, T, MODE>();
     constexpr bool PK = mode_packed_hdr(MODE);
     const T inv_order = (T)tv.inv_order;
-    double acc = 0.0;
-    const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long gstride = (long long)gridDim.x * kBlock;
-    for (long long k = gtid; k < n; k += gstride) {
-        const T xv = __ldcs(x + k);
-        int i;
-        if constexpr (MODE == kGlobalC) i = (int)lk.coarse_cell_wide(xv);
-        else i = lk.leaf(xv);
+
+    auto record_index = [&](T xv) -> int {
+        if constexpr (MODE == kGlobalC) return (int)lk.coarse_cell_wide(xv);
+        else return lk.leaf(xv);
+    };
+    auto load_record = [&](Record<BASIS, ORDER, T>& r, int i) {
+        AI_CHECK(i >= 0 && i < tv.n_records);
+        const T* p = records + i * R;
         if constexpr (mode_uniform_hdr(MODE)) {
-            Record<BASIS, ORDER, T> r;
-            r.template load_uniform<1>(records + i * R, i, (T)tv.u_w, (T)tv.u_lb, (T)tv.u_s);
-            acc += (double)eval_record<BASIS, ORDER, T>(r, xv, inv_order);
+            r.template load_uniform<1>(p, i, (T)tv.u_w, (T)tv.u_lb, (T)tv.u_s);
         } else if constexpr (MODE == kGlobalC) {
-            Record<BASIS, ORDER, T> r;
             unsigned k = 0;
             if constexpr (Record<BASIS, ORDER, T>::HDR == 2) k = (smem[i >> 1] >> ((i & 1) * 4)) & 15u;
-            r.load_compact(records + i * R, (unsigned)i, k, (T)tv.u_w, (T)tv.u_lb, tv.s0_hi, tv.s0_lo);
-            acc += (double)eval_record<BASIS, ORDER, T>(r, xv, inv_order);
+            r.load_compact(p, (unsigned)i, k, (T)tv.u_w, (T)tv.u_lb, tv.s0_hi, tv.s0_lo);
+        } else if constexpr (MODE == kGlobal) {
+            r.load_vec(p);
+        } else if constexpr (PK) {
+            r.template load_packed<1>(p, tv.s0_hi, tv.s0_lo);
         } else {
-            acc += (double)eval_leaf<BASIS, ORDER, T, 1, false, PK>(records + i * R, xv, inv_order, tv.s0_hi, tv.s0_lo);
+            r.template load<1>(p);
         }
+    };
+    auto f = [&](T xv) -> double {
+        Record<BASIS, ORDER, T> r;
+        load_record(r, record_index(xv));
+        return (double)eval_record<BASIS, ORDER, T>(r, xv, inv_order);
+    };
+
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    constexpr int kUnroll = Unroll<T>::value;
+    constexpr long long kTile = (long long)kBlock * kUnroll;       // vectors per tile
+    constexpr int NE = kUnroll * VN;                               // points per thread per tile
+    // scalar head up to the first 16-byte boundary of x (all of it if x is not even element-aligned)
+    const unsigned long long addr = reinterpret_cast<unsigned long long>(x);
+    long long head = (addr % sizeof(T)) ? n : (long long)(((16ull - (addr & 15ull)) & 15ull) / sizeof(T));
+    if (head > n) head = n;
+    const long long nvec = (n - head) / VN;
+    const V* __restrict__ xv = reinterpret_cast<const V*>(x + head);
+    const long long full_tiles = nvec / kTile;
+
+    auto load_tile = [&](V (&buf)[kUnroll], long long tile) {
+        const long long b = tile * kTile + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) buf[u] = ld_stream(xv + b + (long long)u * kBlock);
+    };
+
+    double acc = 0.0;
+    int probe = 0;
+    bool expect_uniform = true;
+    long long tile = blockIdx.x;
+    V in[kUnroll];
+    if (tile < full_tiles) load_tile(in, tile);
+    for (; tile < full_tiles; tile += gridDim.x) {
+        V nxt[kUnroll];
+        const long long next = tile + gridDim.x;
+        if (next < full_tiles) load_tile(nxt, next);
+        T xs[NE];
+        int li[NE];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if constexpr (VN == 4) {
+                xs[4 * u] = in[u].x; xs[4 * u + 1] = in[u].y; xs[4 * u + 2] = in[u].z; xs[4 * u + 3] = in[u].w;
+            } else {
+                xs[2 * u] = in[u].x; xs[2 * u + 1] = in[u].y;
+            }
+        }
+        if constexpr (MODE == kGlobalC) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) li[e] = (int)lk.coarse_cell_wide(xs[e]);
+        } else {
+            lk.leaves(xs, li);
+        }
+        bool uniform = false;
+        if (expect_uniform || probe == 0) {
+            bool same = true;
+#pragma unroll
+            for (int e = 1; e < NE; ++e) same = same && (li[e] == li[0]);
+            uniform = __all_sync(0xffffffffu, same);
+            expect_uniform = uniform;
+            probe = 16;
+        }
+        --probe;
+        if (uniform) {
+            Record<BASIS, ORDER, T> rec;
+            load_record(rec, li[0]);
+            if constexpr (sizeof(T) == 4 && AI_PACKED_F32) {
+#pragma unroll
+                for (int e = 0; e < NE; e += 2) {
+                    const float2 r2 = eval_record_pair<BASIS, ORDER>(rec, rec, xs[e], xs[e + 1]);
+                    acc += (double)r2.x;
+                    acc += (double)r2.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) acc += (double)eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+            }
+        } else {
+            if constexpr (sizeof(T) == 4 && AI_PACKED_F32 == 1) {
+#pragma unroll
+                for (int e = 0; e < NE; e += 2) {
+                    Record<BASIS, ORDER, T> ra, rb;
+                    load_record(ra, li[e]);
+                    load_record(rb, li[e + 1]);
+                    const float2 r2 = eval_record_pair<BASIS, ORDER>(ra, rb, xs[e], xs[e + 1]);
+                    acc += (double)r2.x;
+                    acc += (double)r2.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    Record<BASIS, ORDER, T> rec;
+                    load_record(rec, li[e]);
+                    acc += (double)eval_record<BASIS, ORDER, T>(rec, xs[e], inv_order);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) in[u] = nxt[u];
     }
+    // remainder vectors (less than one tile), spread over the whole grid; scalar head and tail
+    const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kBlock;
+    for (long long v = full_tiles * kTile + gtid; v < nvec; v += gstride) {
+        const V iv = ld_stream(xv + v);
+        if constexpr (VN == 4) { acc += f(iv.x); acc += f(iv.y); acc += f(iv.z); acc += f(iv.w); }
+        else { acc += f(iv.x); acc += f(iv.y); }
+    }
+    for (long long k = gtid; k < head; k += gstride) acc += f(x[k]);
+    for (long long k = head + nvec * VN + gtid; k < n; k += gstride) acc += f(x[k]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     __shared__ double wsum[kBlock / 32];

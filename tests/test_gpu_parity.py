@@ -728,6 +728,8 @@ def test_host_roundtrip_measurement_leaves_the_pipeline_usable():
 def test_eval_sum_variant():
     """The reference's no-"output" kernel variant (generate.py:392-394): y reduced, not stored."""
     for name in ("approx__32o6-p1.19209289551e-06", "gen__cfg3_j0_cheb_o13_f64",
+                 "approx__32o3-p1.19209289551e-06",                  # bank-replicated for evaluation: packed image here
+                 "gen__cfg4_f1_leg_o7_f32", "gen__j0_mono_o13_f64", "mx__leg_o9_f32",
                  "approximations__64o5-p2.22044604925e-14",          # eight-copy layout: reduces from the global image
                  "large__approx__64o3-p2.22044604925e-14"):          # L2-resident
         g = golden(name)
@@ -739,6 +741,19 @@ def test_eval_sum_variant():
         tab.sum_ptr(xd.data_ptr(), res.data_ptr(), xd.numel(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert abs(res.item() - y.sum()) <= 1e-9 * np.abs(y).sum()
+        # any size and any element offset of x (scalar head up to the 16-byte boundary, vectors, tail);
+        # sorted points take the leaf-uniform path
+        esz = x.dtype.itemsize
+        for n, off in ((0, 0), (1, 0), (7, 1), (4099, 3), (1 << 18, 1), ((1 << 20) - 5, 2)):
+            tab.sum_ptr(xd.data_ptr() + off * esz, res.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            want = y[off:off + n]
+            assert abs(res.item() - want.sum()) <= 1e-9 * max(np.abs(want).sum(), 1e-300), (name, n, off)
+        xs = np.sort(x)
+        ys = gpu_eval(tab, xs).astype(np.float64)
+        tab.sum_ptr(to_dev(xs).data_ptr(), res.data_ptr(), len(xs), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert abs(res.item() - ys.sum()) <= 1e-9 * np.abs(ys).sum()
 
 
 # ------------------------------------------------------------------ error behaviour
