@@ -1434,7 +1434,21 @@ index_kernel(const TableView tv, const T* __restrict__ x, int32_t* __restrict__ 
     lk.init(tv, base);
     const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long gstride = (long long)gridDim.x * kBlock;
-    for (long long k = gtid; k < n; k += gstride) idx[k] = lk.leaf_nan_exact(__ldcs(x + k));
+    // kIdxUnroll coalesced loads in flight per thread (one point per thread per iteration left a single
+    // load in flight: latency-bound at a fifth of the evaluation kernel's rate), lookups of the whole
+    // batch together so that their dependent chains interleave
+    constexpr int kIdxUnroll = 8;
+    long long k = gtid;
+    for (; k + (kIdxUnroll - 1) * gstride < n; k += kIdxUnroll * gstride) {
+        T xs[kIdxUnroll];
+        int li[kIdxUnroll];
+#pragma unroll
+        for (int u = 0; u < kIdxUnroll; ++u) xs[u] = __ldcs(x + k + u * gstride);
+        lk.template true_leaves<kIdxUnroll>(xs, li);
+#pragma unroll
+        for (int u = 0; u < kIdxUnroll; ++u) __stcs(idx + k + u * gstride, (xs[u] != xs[u]) ? lk.lmax : li[u]);   // NaN: see leaf_nan_exact
+    }
+    for (; k < n; k += gstride) idx[k] = lk.leaf_nan_exact(__ldcs(x + k));
 }
 
 // ------------------------------------------------------------------------- launch plumbing

@@ -59,16 +59,21 @@ def main():
         res = torch.zeros(1, dtype=torch.float64, device="cuda")
         te = time_ms(lambda: tab.eval_ptr(x.data_ptr(), y.data_ptr(), n, s))
         ts = time_ms(lambda: tab.sum_ptr(x.data_ptr(), res.data_ptr(), n, s))
+        idx = torch.empty(n, dtype=torch.int32, device="cuda")
+        ti = time_ms(lambda: tab.index_ptr(x.data_ptr(), idx.data_ptr(), n, s))
+        del idx
         want = float(y.double().sum())
         got = float(res.item())
         rel = abs(got - want) / max(1.0, abs(want))
         esz = f.dtype.itemsize
         row = {"table": name, "dtype": "f32" if esz == 4 else "f64", "eval_ms": te, "sum_ms": ts,
                "eval_gpts": n / te / 1e6, "sum_gpts": n / ts / 1e6, "sum_frac_of_hbm_reading_x": n * esz / (ts * 1e-3) / 1e9 / hbm,
-               "sum_rel_diff_vs_sum_of_eval": rel}
+               "sum_rel_diff_vs_sum_of_eval": rel, "index_ms": ti, "index_gpts": n / ti / 1e6,
+               "index_frac_of_hbm": n * (esz + 4) / (ti * 1e-3) / 1e9 / hbm}
         rows.append(row)
-        print("%-44s %4s | %9.3f %8.1f | %9.3f %8.1f %7.1f | %.2e" % (name[:44], row["dtype"], te, row["eval_gpts"], ts,
-                                                                    row["sum_gpts"], 100 * row["sum_frac_of_hbm_reading_x"], rel))
+        print("%-44s %4s | %9.3f %8.1f | %9.3f %8.1f %7.1f | %.2e | index %7.3f ms %7.1f Gpt/s %5.1f%% of HBM"
+              % (name[:44], row["dtype"], te, row["eval_gpts"], ts, row["sum_gpts"], 100 * row["sum_frac_of_hbm_reading_x"], rel,
+                 ti, row["index_gpts"], 100 * row["index_frac_of_hbm"]))
         tab.close()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"n": n, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", args.tag + ".json"), "w"), indent=1)
