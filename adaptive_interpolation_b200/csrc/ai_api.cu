@@ -1183,15 +1183,15 @@ int launch_eval_t(const ai_table* t, const T* x, T* y, int64_t n, cudaStream_t s
     constexpr int VN = ai::Vec<T>::N;
     const uintptr_t ax = reinterpret_cast<uintptr_t>(x), ay = reinterpret_cast<uintptr_t>(y);
     if ((ax % sizeof(T)) || (ay % sizeof(T))) return fail(AI_ERR_INVALID, "x / y not aligned to the element size");
-    long long head, nvec;
-    if ((ax % 16) == (ay % 16)) {
-        head = (long long)(((16 - (ax % 16)) % 16) / sizeof(T));
-        if (head > n) head = n;
-        nvec = (n - head) / VN;
-    } else {            // x and y can never be 16-byte aligned together: scalar path
-        head = n;
-        nvec = 0;
-    }
+    // scalar head up to the first 16-byte boundary of y, then 16-byte vectors, then a scalar tail.  When
+    // x and y can never be 16-byte aligned together (x is a view that starts one element into its
+    // buffer, say) the stores stay 128-bit and the kernel reads the tile's x element by element; routing
+    // the whole call through the scalar loop instead cost a factor of six (profiles/r3_misaligned_*.txt).
+    long long head = (long long)(((16 - (ay % 16)) % 16) / sizeof(T));
+    if (head > n) head = n;
+    const long long nvec = (n - head) / VN;
+    ai::TableView view = t->view;
+    view.x_elem_loads = ((ax % 16) != (ay % 16)) ? 1 : 0;
     ai::LaunchCfg cfg;
     const long long tile_elems = (long long)ai::kBlock * ai::Unroll<T>::value * VN;
     const long long want = (n + tile_elems - 1) / tile_elems;
@@ -1202,13 +1202,13 @@ int launch_eval_t(const ai_table* t, const T* x, T* y, int64_t n, cudaStream_t s
     cudaError_t e;
     const int m = t->mode;
     if constexpr (sizeof(T) == 4) {
-        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f32(t->order, m, cfg, t->view, x, y, n, head, nvec);
-        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f32(t->order, m, cfg, t->view, x, y, n, head, nvec);
-        else e = ai::launch_eval_mono_f32(t->order, m, cfg, t->view, x, y, n, head, nvec);
+        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f32(t->order, m, cfg, view, x, y, n, head, nvec);
+        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f32(t->order, m, cfg, view, x, y, n, head, nvec);
+        else e = ai::launch_eval_mono_f32(t->order, m, cfg, view, x, y, n, head, nvec);
     } else {
-        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f64(t->order, m, cfg, t->view, x, y, n, head, nvec);
-        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f64(t->order, m, cfg, t->view, x, y, n, head, nvec);
-        else e = ai::launch_eval_mono_f64(t->order, m, cfg, t->view, x, y, n, head, nvec);
+        if (t->basis == ai::kCheb) e = ai::launch_eval_cheb_f64(t->order, m, cfg, view, x, y, n, head, nvec);
+        else if (t->basis == ai::kLeg) e = ai::launch_eval_leg_f64(t->order, m, cfg, view, x, y, n, head, nvec);
+        else e = ai::launch_eval_mono_f64(t->order, m, cfg, view, x, y, n, head, nvec);
     }
     if (e != cudaSuccess) return fail(AI_ERR_CUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));
     return AI_OK;

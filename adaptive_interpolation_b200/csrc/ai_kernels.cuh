@@ -183,6 +183,10 @@ struct TableView {
     int path_zbias;                // entry = row * path_rowlen + clz(V ^ target[row]) - path_zbias
     int path_toff;                 // byte offset of the rows inside first[]
     int path_t16;                  // rows hold 16-bit leaf ordinals (more than 256 leaves), else bytes
+    // per LAUNCH (set by launch_eval_t on its copy of the view): x + head is not 16-byte aligned although
+    // y + head is (x and y can never be aligned together, e.g. x is a view that starts one element into
+    // its buffer): the tile's x comes from element loads instead of 128-bit ones
+    int x_elem_loads;
 };
 
 // ---------------------------------------------------------------------------------- helpers
@@ -961,12 +965,25 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     constexpr int kUnroll = Unroll<T>::value;                      // shadows the namespace constant
     constexpr long long kTile = (long long)kBlock * kUnroll;       // vectors per tile
     constexpr int NE = kUnroll * VN;                               // points per thread per tile
-    const long long full_tiles = nvec / kTile;
 
     auto load_tile = [&](V (&buf)[kUnroll], long long tile) {
         const long long base = tile * kTile + threadIdx.x;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) buf[u] = ld_stream(xv + base + (long long)u * kBlock);
+    };
+    // x_elem_loads (x + head is not 16-byte aligned although y + head is): no tile takes the 128-bit
+    // loads; every vector goes through the grid-stride loop below, which then reads its VN elements
+    // one by one (kept OUT of the tile loop: even predicated off, the element loads cost the aligned
+    // path 18% -- measured)
+    const bool x_elem = tv.x_elem_loads != 0;
+    const long long full_tiles = x_elem ? 0 : nvec / kTile;
+    auto load_vec_x = [&](long long v) -> V {
+        if (!x_elem) return ld_stream(xv + v);
+        const T* __restrict__ p = x + head + v * VN;
+        V r;
+        if constexpr (VN == 4) { r.x = __ldg(p); r.y = __ldg(p + 1); r.z = __ldg(p + 2); r.w = __ldg(p + 3); }
+        else { r.x = __ldg(p); r.y = __ldg(p + 1); }
+        return r;
     };
 
     [[maybe_unused]] int probe = 0;          // AI_UNIFORM_PATH == 2: tiles until the next probe
@@ -1079,8 +1096,9 @@ eval_kernel(const TableView tv, const SelectTable<T, MODE> sel, const T* __restr
     // remainder vectors (less than one tile), spread over the whole grid
     const long long gtid = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long gstride = (long long)gridDim.x * kBlock;
+#pragma unroll 2
     for (long long v = full_tiles * kTile + gtid; v < nvec; v += gstride) {
-        V in = ld_stream(xv + v), out;
+        V in = load_vec_x(v), out;
         if constexpr (VN == 4) {
             out.x = f(in.x); out.y = f(in.y); out.z = f(in.z); out.w = f(in.w);
         } else {

@@ -620,8 +620,14 @@ def test_million_points_vs_oracle(name):
 
 
 # ------------------------------------------------------------------ ragged sizes and alignment
-@pytest.mark.parametrize("name", ["approx__32o7-p1.19209289551e-06", "approx__64o7-p1.19209289551e-06"])
+@pytest.mark.parametrize("name", ["approx__32o7-p1.19209289551e-06", "approx__64o7-p1.19209289551e-06",
+                                  "approx__32o3-p1.19209289551e-06",            # bank-private copies
+                                  "approx__64o13-p1.19209289551e-06",           # two leaves: select
+                                  "gen__cfg4_f1_leg_o7_f64",                    # eight copies + path lookup
+                                  "large__approx__64o3-p2.22044604925e-14"])    # L2-resident compact
 def test_sizes_and_misalignment(name):
+    """Every split of [0, n) into scalar head / 16-byte vectors / tail, x and y offset independently:
+    when they cannot be aligned together the stores stay 128-bit and x is read element by element."""
     g = golden(name)
     tab = dev_table(name)
     rng = np.random.default_rng(5)
