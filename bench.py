@@ -601,6 +601,33 @@ def main():
             clocks.mark()
             tot1, k1, k1min = time_table(t1, x1, y1, 50, 5)
             launches_configs += 50
+            # the same launch 64 times inside ONE CUDA graph: GPU time per launch without the host's enqueue
+            # gaps (a single launch between two events is bound by the Python / driver enqueue path)
+            graph_ms, graph_err = None, ""
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(stream)
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(cg, stream=side):
+                        for _ in range(64):
+                            t1.eval_ptr(x1.data_ptr(), y1.data_ptr(), n1, torch.cuda.current_stream().cuda_stream)
+                stream.wait_stream(side)
+                with torch.cuda.stream(stream):
+                    for _ in range(3):
+                        cg.replay()
+                    g0, g1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record(stream)
+                    for _ in range(10):
+                        cg.replay()
+                    g1e.record(stream)
+                torch.cuda.synchronize()
+                graph_ms = g0.elapsed_time(g1e) / 640.0
+                launches_configs += 13 * 64
+                del cg
+            except Exception as exc:                      # noqa: BLE001 -- an optional extra record, never fatal
+                graph_ms = None
+                graph_err = repr(exc)[:200]
             rec1 = {"config": "cfg1", "workload": "gen__cfg1_sinsin_cheb_o3_f64", "points": n1, "points_per_gpu": n1,
                     "point_distribution": "linspace(0, 10, 2^20, endpoint=False) (SURVEY 8(d)1); every rank evaluates the whole "
                                           "array (2^20 points are one launch of ~10 us: not sharded)",
@@ -608,6 +635,13 @@ def main():
                     "value": n1 / (k1 * 1e-3) / 1e9, "unit": UNIT, "steps": 50, "kernel_ms": k1, "kernel_ms_min": k1min,
                     "frac": frac_of_hbm(n1, 8, k1), "clocks": clocks.mark(),
                     "note": "launch-latency bound at this size (16 MiB of traffic); the same table at 2^28 points is in cfg5"}
+            if graph_ms:
+                rec1["in_cuda_graph"] = {"launches_per_graph": 64, "kernel_ms": graph_ms, "value": n1 / (graph_ms * 1e-3) / 1e9,
+                                         "frac": frac_of_hbm(n1, 8, graph_ms),
+                                         "note": "64 launches captured in one CUDA graph, 10 replays: per-launch time without "
+                                                 "the host enqueue path"}
+            else:
+                rec1["in_cuda_graph"] = {"unavailable": graph_err}
             if rank == 0 and world == 1 and not args.no_cpu:
                 x1_np = x1.cpu().numpy()
                 y_ref, secs = reference_evaluate(g1, x1_np)
