@@ -737,6 +737,16 @@ def main():
         cpu = time_cpu_baseline(g)
         cpu["b_ref"] = b_ref
         from oracle import oracle_np
+        # B-np (SURVEY 8(d) CPU baseline ii): the vectorised numpy restatement of Approximator.evaluate,
+        # one core, 2^24 uniform random points of the headline workload
+        x_np24, _ = make_cpu_sample(g, 24)
+        t0 = time.perf_counter()
+        oracle_np.evaluate(flat.breaks, flat.coef, flat.basis, flat.order, x_np24)
+        secs_np = time.perf_counter() - t0
+        cpu["b_np"] = {"value": x_np24.size / secs_np / 1e9, "unit": UNIT, "cores": 1, "points": int(x_np24.size),
+                       "seconds": secs_np, "impl": "oracle/oracle_np.py: vectorised numpy restatement of "
+                                                   "Approximator.evaluate (approximator.py:273-296), one pass"}
+        del x_np24
         y_o = oracle_np.evaluate(flat.breaks, flat.coef, flat.basis, flat.order, xs_np)
         cond = oracle_np.error_scale(flat.breaks, flat.coef, flat.basis, flat.order, xs_np)
         ok = np.isfinite(cond) & np.isfinite(y_o)
