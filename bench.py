@@ -678,21 +678,26 @@ def main():
             for nm in ("gen__cfg4_f1_leg_o7_f32", "gen__cfg4_f1_leg_o7_f64"):
                 configs.append(run_config("cfg4", nm, (1 << 28) * world, "clustered", False))
             # cfg5: every saved table (and the refitted missing ones) at 2^30 global points
+            # (+ the monomial / Legendre tables the reference's fitter constructs for J0 on [0,20])
+            gen5 = ("gen__j0_mono_o5_f64", "gen__j0_mono_o13_f64", "gen__j0_leg_o7_f32", "gen__j0_leg_o7_f64",
+                    "gen__j0_leg_o6_remez_f64")
             names5 = [nm for nm in golden_io.golden_names()
-                      if nm.startswith(("approx__", "approximations__", "large__"))]
+                      if nm.startswith(("approx__", "approximations__", "large__")) or nm in gen5]
             rows = []
             for nm in names5:
                 rec = run_config("cfg5", nm, 1 << CFG5_GLOBAL_LOG2, "uniform", True, steps=5)
-                rows.append({k: rec[k] for k in ("workload", "dtype", "order", "leaves", "residency", "value",
+                rows.append({k: rec[k] for k in ("workload", "dtype", "basis", "order", "leaves", "residency", "value",
                                                  "kernel_ms", "frac")})
                 rows[-1]["sm_mhz"] = rec["clocks"].get("sm_mhz")
                 rows[-1]["reasons"] = rec["clocks"].get("reasons")
             fr = np.array([r["frac"] for r in rows])
-            lo7 = np.array([r["frac"] for r in rows if r["order"] <= 7 and not r["workload"].startswith("large__")])
+            lo7 = np.array([r["frac"] for r in rows if r["order"] <= 7 and r["workload"].startswith(("approx__", "approximations__"))])
             configs.append({"config": "cfg5", "workload": "all %d saved tables (approx/, approximations/) + %d large tables "
-                            "refitted with the reference's fitter (.MISSING_LARGE_BLOBS and one more)"
-                            % (sum(not r["workload"].startswith("large__") for r in rows),
-                               sum(r["workload"].startswith("large__") for r in rows)),
+                            "refitted with the reference's fitter (.MISSING_LARGE_BLOBS and one more) + %d monomial / Legendre "
+                            "tables fitted by the reference's fitter for J0 on [0,20] (SURVEY 8(d)5)"
+                            % (sum(r["workload"].startswith(("approx__", "approximations__")) for r in rows),
+                               sum(r["workload"].startswith("large__") for r in rows),
+                               sum(r["workload"].startswith("gen__") for r in rows)),
                             "points": 1 << CFG5_GLOBAL_LOG2, "points_per_gpu": shard_points(1 << CFG5_GLOBAL_LOG2),
                             "point_distribution": "uniform", "scaling": "strong", "steps": 5,
                             "frac_min": float(fr.min()), "frac_median": float(np.median(fr)), "frac_max": float(fr.max()),
