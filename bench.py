@@ -70,8 +70,8 @@ SUSTAINED_SECONDS = 2.0
 CONFIG_IDLE_SECONDS = 0.25      # idle gap before each per-config measurement (the power window recovers)
 
 NCU_SUMMARIES = {   # workload -> committed `ncu --set full` summary (tools/ncu_summary.py)
-    "cfg2_j0_cheb_o6_f32": "r2_ncu_cfg2.json",
-    "cfg3_j0_cheb_o13_f64": "r2_ncu_cfg3.json",
+    "cfg2_j0_cheb_o6_f32": "r3_ncu_cfg2.json",
+    "cfg3_j0_cheb_o13_f64": "r3_ncu_cfg3.json",
 }
 
 
