@@ -9,7 +9,9 @@
 #include "ai_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +22,11 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace ai {
 // one lock for every get-then-set of a kernel's dynamic shared memory limit (ai_inst.cuh, index_entry)
@@ -116,6 +122,98 @@ int grid_budget(int dflt) {
 }
 constexpr int kHostSlots = 4;          // host pipeline depth (slots actually used: AI_B200_HOST_SLOTS)
 
+// Fork-join pool of host threads for the bounce copies of the staged host pipeline (pageable caller
+// buffers).  run() hands every participant (the workers and the caller) one contiguous share of every
+// job and returns when ALL workers have reported for this batch, so no thread can still be touching a
+// buffer of batch g when batch g + 1 is set up.
+class CopyPool {
+public:
+    struct Job { char* dst; const char* src; size_t bytes; };
+    explicit CopyPool(int participants) : n_(std::max(1, participants)) {
+        for (int w = 0; w + 1 < n_; ++w) th_.emplace_back([this, w] { worker(w); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_start_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    CopyPool(const CopyPool&) = delete;
+    CopyPool& operator=(const CopyPool&) = delete;
+    void run(const Job* jobs, int nj) {
+        if (nj <= 0) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int j = 0; j < nj; ++j) jobs_[j] = jobs[j];
+            njobs_ = nj; finished_ = 0; ++gen_;
+        }
+        cv_start_.notify_all();
+        share(jobs, nj, n_ - 1, n_);
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return finished_ == (int)th_.size(); });
+    }
+
+private:
+    static void share(const Job* jobs, int nj, int who, int n) {
+        for (int j = 0; j < nj; ++j) {
+            const size_t per = ((jobs[j].bytes + (size_t)n - 1) / (size_t)n + 4095) & ~(size_t)4095;   // page-aligned shares
+            const size_t lo = std::min(jobs[j].bytes, per * (size_t)who), hi = std::min(jobs[j].bytes, lo + per);
+            if (hi > lo) stream_copy(jobs[j].dst + lo, jobs[j].src + lo, hi - lo);
+        }
+    }
+    // memcpy with non-temporal stores: the destination (a bounce buffer the DMA engine reads next, or
+    // the caller's y) is not read again by this core, so the write-allocate traffic of ordinary stores
+    // is wasted host memory bandwidth -- and host memory bandwidth is what bounds this path
+    static void stream_copy(char* dst, const char* src, size_t bytes) {
+#if defined(__x86_64__)
+        const size_t head = std::min(bytes, (size_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+        if (head) { std::memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
+        const size_t blocks = bytes / 64;
+        for (size_t b = 0; b < blocks; ++b) {
+            const __m128i v0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 0);
+            const __m128i v1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 1);
+            const __m128i v2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 2);
+            const __m128i v3 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 3);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 0, v0);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 1, v1);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 2, v2);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 3, v3);
+            src += 64; dst += 64;
+        }
+        _mm_sfence();
+        if (bytes & 63) std::memcpy(dst, src, bytes & 63);
+#else
+        std::memcpy(dst, src, bytes);
+#endif
+    }
+    void worker(int who) {
+        uint64_t seen = 0;
+        for (;;) {
+            Job local[2];
+            int nj = 0;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_start_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_; nj = njobs_;
+                for (int j = 0; j < nj; ++j) local[j] = jobs_[j];
+            }
+            share(local, nj, who, n_);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (++finished_ == (int)th_.size()) cv_done_.notify_one();
+            }
+        }
+    }
+    const int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_start_, cv_done_;
+    uint64_t gen_ = 0;
+    int finished_ = 0, njobs_ = 0;
+    bool stop_ = false;
+    Job jobs_[2] = {};
+};
+
 struct HostPipe {
     bool ready = false;
     int64_t chunk = 0;                 // elements per chunk
@@ -125,6 +223,11 @@ struct HostPipe {
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t in_done[kHostSlots] = {}, k_done[kHostSlots] = {}, out_done[kHostSlots] = {};
     cudaEvent_t k_start[kHostSlots] = {};
+    // staged path (pageable caller buffers): pinned bounce buffers per slot and the copy threads
+    void* hin[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
+    void* hout[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
+    size_t elem = 0;
+    std::unique_ptr<CopyPool> pool;
     std::mutex mu;
 };
 
@@ -1398,6 +1501,7 @@ int pipe_init_body(ai_table* t, size_t elem) {
     if (const char* e = std::getenv("AI_B200_HOST_CHUNK_MB")) { const long v = std::atol(e); if (v >= 1 && v <= 1024) mib = v; }
     if (const char* e = std::getenv("AI_B200_HOST_SLOTS")) { const long v = std::atol(e); if (v >= 2 && v <= kHostSlots) p.slots = (int)v; }
     p.chunk = (int64_t)(mib << 20) / (int64_t)elem;
+    p.elem = elem;
     for (int s = 0; s < p.slots; ++s) {
         AI_CUDA(cudaMalloc(&p.dx[s], (size_t)p.chunk * elem));
         AI_CUDA(cudaMalloc(&p.dy[s], (size_t)p.chunk * elem));
@@ -1422,6 +1526,9 @@ void pipe_destroy(ai_table* t) {
         if (p.out_done[s]) cudaEventDestroy(p.out_done[s]);
         if (p.k_start[s]) cudaEventDestroy(p.k_start[s]);
         if (p.k_done[s]) cudaEventDestroy(p.k_done[s]);
+        if (p.hin[s]) cudaFreeHost(p.hin[s]);
+        if (p.hout[s]) cudaFreeHost(p.hout[s]);
+        p.hin[s] = p.hout[s] = nullptr;
         p.dx[s] = p.dy[s] = nullptr;
         p.in_done[s] = p.out_done[s] = p.k_start[s] = p.k_done[s] = nullptr;
     }
@@ -1429,6 +1536,7 @@ void pipe_destroy(ai_table* t) {
     if (p.s_k) cudaStreamDestroy(p.s_k);
     if (p.s_out) cudaStreamDestroy(p.s_out);
     p.s_in = p.s_k = p.s_out = nullptr;
+    p.pool.reset();
     p.ready = false;
 }
 
@@ -1474,6 +1582,90 @@ int host_pipeline_pass(ai_table* t, const T* x, T* y, int64_t n, bool with_kerne
     return AI_OK;
 }
 
+// Is a caller's host buffer something cudaMemcpyAsync can DMA from / to directly (page-locked,
+// managed, or in fact device memory)?  Ordinary (pageable) memory is not: the driver then stages every
+// copy through its own buffer, synchronously and from one thread -- 6.6 GB/s per direction against 44
+// for pinned buffers on this pool's hosts (tools/host_pageable_bench.py).
+bool directly_copyable(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice;
+}
+
+int host_threads_default() {
+    if (const char* e = std::getenv("AI_B200_HOST_THREADS")) { const long v = std::atol(e); if (v >= 1 && v <= 256) return (int)v; }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(16u, std::max<unsigned>(1u, hw));
+}
+
+// The pipeline for PAGEABLE caller buffers (what a numpy caller of the reference-style binding passes):
+// the library's own page-locked bounce buffers, filled / drained by a pool of host threads, so that
+// the DMA engines run asynchronously at their pinned rate while the host copies of the neighbouring
+// chunks proceed.  Iteration c: [copy x chunk c -> hin  ||  copy hout -> y of chunk c - lag] on all
+// threads, then enqueue chunk c (H2D, kernel, D2H); the GPU works on chunk c - 1 meanwhile.
+template <typename T>
+int host_pipeline_pass_staged(ai_table* t, const T* x, T* y, int64_t n, bool with_kernel, double* ms_total,
+                              bool stage_in, bool stage_out) {
+    HostPipe& p = t->pipe;
+    const size_t cbytes = (size_t)p.chunk * sizeof(T);
+    for (int s = 0; s < p.slots; ++s) {
+        if (stage_in && !p.hin[s]) AI_CUDA(cudaHostAlloc(&p.hin[s], cbytes, cudaHostAllocDefault));
+        if (stage_out && !p.hout[s]) AI_CUDA(cudaHostAlloc(&p.hout[s], cbytes, cudaHostAllocDefault));
+    }
+    if (!p.pool) p.pool.reset(new CopyPool(host_threads_default()));
+    const int64_t nchunks = (n + p.chunk - 1) / p.chunk;
+    const int lag = p.slots - 1;                          // < slots: a slot is drained before it is refilled
+    for (int64_t c = 0; c < nchunks + lag; ++c) {
+        CopyPool::Job jobs[2];
+        int nj = 0;
+        const int s = (int)(c % p.slots);
+        const int64_t off = c * p.chunk, m = (c < nchunks) ? std::min<int64_t>(p.chunk, n - off) : 0;
+        if (c < nchunks) {
+            if (c >= p.slots) {
+                // slot reuse: everything of chunk c - slots has drained (its copy to y ran at iteration c - 1)
+                AI_CUDA(cudaEventSynchronize(p.out_done[s]));
+                float ms = 0.f;
+                AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
+                *ms_total += ms;
+            }
+            if (stage_in) jobs[nj++] = {static_cast<char*>(p.hin[s]), reinterpret_cast<const char*>(x + off), (size_t)m * sizeof(T)};
+        }
+        const int64_t d = c - lag;
+        if (stage_out && d >= 0 && d < nchunks) {
+            const int sd = (int)(d % p.slots);
+            const int64_t offd = d * p.chunk, md = std::min<int64_t>(p.chunk, n - offd);
+            AI_CUDA(cudaEventSynchronize(p.out_done[sd]));
+            jobs[nj++] = {reinterpret_cast<char*>(y + offd), static_cast<const char*>(p.hout[sd]), (size_t)md * sizeof(T)};
+        }
+        p.pool->run(jobs, nj);
+        if (c < nchunks) {
+            const void* src = stage_in ? p.hin[s] : static_cast<const void*>(x + off);
+            void* dst = stage_out ? p.hout[s] : static_cast<void*>(y + off);
+            AI_CUDA(cudaMemcpyAsync(p.dx[s], src, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, p.s_in));
+            AI_CUDA(cudaEventRecord(p.in_done[s], p.s_in));
+            AI_CUDA(cudaStreamWaitEvent(p.s_k, p.in_done[s], 0));
+            AI_CUDA(cudaEventRecord(p.k_start[s], p.s_k));
+            if (with_kernel) {
+                const int rc = launch_eval_t<T>(t, static_cast<const T*>(p.dx[s]), static_cast<T*>(p.dy[s]), m, p.s_k);
+                if (rc) return rc;
+            }
+            AI_CUDA(cudaEventRecord(p.k_done[s], p.s_k));
+            AI_CUDA(cudaStreamWaitEvent(p.s_out, p.k_done[s], 0));
+            AI_CUDA(cudaMemcpyAsync(dst, p.dy[s], (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, p.s_out));
+            AI_CUDA(cudaEventRecord(p.out_done[s], p.s_out));
+        }
+    }
+    AI_CUDA(cudaStreamSynchronize(p.s_out));
+    const int64_t first_pending = std::max<int64_t>(0, nchunks - p.slots);
+    for (int64_t c = first_pending; c < nchunks; ++c) {
+        const int s = (int)(c % p.slots);
+        float ms = 0.f;
+        AI_CUDA(cudaEventElapsedTime(&ms, p.k_start[s], p.k_done[s]));
+        *ms_total += ms;
+    }
+    return AI_OK;
+}
+
 template <typename T>
 int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_ms, bool with_kernel = true) {
     if (kernel_ms) *kernel_ms = 0.0;
@@ -1489,7 +1681,12 @@ int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_m
     int rc = pipe_init(t, sizeof(T));
     if (rc) return rc;
     double ms_total = 0.0;
-    rc = host_pipeline_pass<T>(t, x, y, n, with_kernel, &ms_total);
+    // pageable caller buffers go through the library's pinned bounce buffers (AI_B200_HOST_STAGING=0: never)
+    const char* stg = std::getenv("AI_B200_HOST_STAGING");
+    const bool staging = !(stg && stg[0] == '0');
+    const bool stage_in = staging && !directly_copyable(x), stage_out = staging && !directly_copyable(y);
+    if (stage_in || stage_out) rc = host_pipeline_pass_staged<T>(t, x, y, n, with_kernel, &ms_total, stage_in, stage_out);
+    else rc = host_pipeline_pass<T>(t, x, y, n, with_kernel, &ms_total);
     if (rc) {
         // no copy into (or out of) the caller's buffers may still be in flight when we return
         const std::string msg = g_err;

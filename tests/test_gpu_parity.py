@@ -694,14 +694,26 @@ def test_oversized_leaf_count_is_an_error_not_a_crash():
 @pytest.mark.parametrize("name,n", [("approx__32o6-p1.19209289551e-06", (1 << 25) + 12345),
                                     ("approx__64o7-p2.22044604925e-14", (1 << 23) + 77),
                                     ("approx__32o6-p1.19209289551e-06", 1000)])
-def test_eval_host_pipeline(name, n):
-    """ai_eval_host_*: chunked H2D / kernel / D2H; more chunks than pipeline slots."""
+def test_eval_host_pipeline(name, n, monkeypatch):
+    """ai_eval_host_*: chunked H2D / kernel / D2H; more chunks than pipeline slots.  Pageable numpy
+    arrays go through the library's pinned bounce buffers and copy threads (the staged path), pinned
+    ones are copied from / to directly; any mix gives the same bits."""
     g = golden(name)
     tab = dev_table(name)
     x = np.random.default_rng(3).uniform(0, 20, n).astype(g.dtype)
     y, ms = tab.eval_host(x)
     assert ms > 0
     assert np.array_equal(y, gpu_eval(tab, x))
+    # an unaligned pageable view, a few copy threads, and the unstaged route for pageable memory
+    big = np.empty(n + 3, dtype=g.dtype)
+    big[1:n + 1] = x
+    out = np.full(n + 5, np.nan, dtype=g.dtype)
+    tab.eval_host(big[1:n + 1], out[3:n + 3])
+    assert np.array_equal(out[3:n + 3], y) and np.all(np.isnan(out[:3])) and np.all(np.isnan(out[n + 3:]))
+    monkeypatch.setenv("AI_B200_HOST_STAGING", "0")
+    y0, _ = tab.eval_host(x)
+    assert np.array_equal(y0, y)
+    monkeypatch.delenv("AI_B200_HOST_STAGING")
     # pinned buffers from the library give the same result
     p = ctypes.c_void_p()
     _cabi.check(_cabi.lib().ai_host_alloc(ctypes.byref(p), 2 * x.nbytes))
@@ -710,6 +722,12 @@ def test_eval_host_pipeline(name, n):
         buf[:n] = x
         y2, _ = tab.eval_host(buf[:n], buf[n:])
         assert np.array_equal(y2, y)
+        # mixed: pinned x with a pageable y (only the output is staged), and the other way round
+        y3, _ = tab.eval_host(buf[:n])
+        assert np.array_equal(y3, y)
+        buf[n:] = 0
+        tab.eval_host(x, buf[n:])
+        assert np.array_equal(buf[n:], y)
     finally:
         _cabi.check(_cabi.lib().ai_host_free(p))
 
