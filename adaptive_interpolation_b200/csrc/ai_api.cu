@@ -1683,7 +1683,9 @@ int host_entry(const ai_table* ct, const T* x, T* y, int64_t n, double* kernel_m
     double ms_total = 0.0;
     // pageable caller buffers go through the library's pinned bounce buffers (AI_B200_HOST_STAGING=0: never)
     const char* stg = std::getenv("AI_B200_HOST_STAGING");
-    const bool staging = !(stg && stg[0] == '0');
+    // (not for small calls: below 1 MiB the driver's own staging costs microseconds, while the first staged
+    // call allocates the bounce buffers and starts the copy threads)
+    const bool staging = !(stg && stg[0] == '0') && (size_t)n * sizeof(T) >= ((size_t)1 << 20);
     const bool stage_in = staging && !directly_copyable(x), stage_out = staging && !directly_copyable(y);
     if (stage_in || stage_out) rc = host_pipeline_pass_staged<T>(t, x, y, n, with_kernel, &ms_total, stage_in, stage_out);
     else rc = host_pipeline_pass<T>(t, x, y, n, with_kernel, &ms_total);
