@@ -28,7 +28,7 @@ EXPORTS = [
     "ai_eval_f32", "ai_eval_f64", "ai_eval_index_f32", "ai_eval_index_f64",
     "ai_eval_sum_f32", "ai_eval_sum_f64", "ai_eval_multi_f32", "ai_eval_multi_f64",
     "ai_eval_host_f32", "ai_eval_host_f64",
-    "ai_host_alloc", "ai_host_free", "ai_measure_fma_peak", "ai_copy_f32", "ai_measure_host_roundtrip",
+    "ai_host_alloc", "ai_host_free", "ai_host_copy", "ai_measure_fma_peak", "ai_copy_f32", "ai_measure_host_roundtrip",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
         getattr(L, name).argtypes = [vp, vp, vp, i64, ctypes.POINTER(ctypes.c_double)]
     L.ai_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
     L.ai_host_free.argtypes = [vp]
+    L.ai_host_copy.argtypes = [vp, vp, i64, i32]
     L.ai_measure_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.ai_copy_f32.argtypes = [vp, vp, i64, i32, vp]
     L.ai_measure_host_roundtrip.argtypes = [vp, vp, vp, i64]

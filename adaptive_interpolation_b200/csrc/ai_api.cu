@@ -1612,7 +1612,13 @@ int host_pipeline_pass_staged(ai_table* t, const T* x, T* y, int64_t n, bool wit
         if (stage_in && !p.hin[s]) AI_CUDA(cudaHostAlloc(&p.hin[s], cbytes, cudaHostAllocDefault));
         if (stage_out && !p.hout[s]) AI_CUDA(cudaHostAlloc(&p.hout[s], cbytes, cudaHostAllocDefault));
     }
-    if (!p.pool) p.pool.reset(new CopyPool(host_threads_default()));
+    if (!p.pool) {
+        try {
+            p.pool.reset(new CopyPool(host_threads_default()));
+        } catch (const std::exception& e) {          // no exception may cross the C ABI
+            return fail(AI_ERR_UNSUPPORTED, "cannot start the host copy threads: %s", e.what());
+        }
+    }
     const int64_t nchunks = (n + p.chunk - 1) / p.chunk;
     const int lag = p.slots - 1;                          // < slots: a slot is drained before it is refilled
     for (int64_t c = 0; c < nchunks + lag; ++c) {
@@ -1984,6 +1990,19 @@ int ai_host_alloc(void** p, int64_t bytes) {
     if (!p || bytes < 0) return fail(AI_ERR_INVALID, "bad arguments");
     AI_CUDA(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault));
     return AI_OK;
+}
+
+int ai_host_copy(void* dst, const void* src, int64_t bytes, int threads) {
+    return guarded([&]() -> int {
+        if (bytes < 0) return fail(AI_ERR_INVALID, "bytes = %lld is negative", (long long)bytes);
+        if (bytes == 0) return AI_OK;
+        if (!dst || !src) return fail(AI_ERR_INVALID, "dst or src is NULL");
+        if (threads > 256) return fail(AI_ERR_INVALID, "threads = %d is more than 256", threads);
+        CopyPool pool(threads > 0 ? threads : host_threads_default());
+        const CopyPool::Job job = {static_cast<char*>(dst), static_cast<const char*>(src), (size_t)bytes};
+        pool.run(&job, 1);
+        return AI_OK;
+    });
 }
 
 int ai_host_free(void* p) {

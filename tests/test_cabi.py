@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from adaptive_interpolation_b200 import _cabi, build
@@ -62,3 +63,21 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libai_b200.so")
     with pytest.raises(ImportError):
         _cabi.lib()
+
+
+def test_host_copy_pool_copies_every_byte(lib):
+    """ai_host_copy: the threaded, non-temporal-store copy the staged host pipeline runs on pageable caller
+    buffers (page-aligned shares, 16-byte-aligned streaming stores with memcpy head / tail).  Any size,
+    any alignment of source and destination, any thread count; nothing outside [dst, dst + bytes) written."""
+    L = _cabi.lib()
+    rng = np.random.default_rng(0)
+    src_buf = rng.integers(0, 256, (1 << 22) + 256, dtype=np.uint8)
+    for nbytes in (0, 1, 15, 16, 17, 63, 64, 65, 4095, 4096, 4097, 65536 + 3, (1 << 20) + 11, (1 << 22) - 7):
+        for so, do, threads in ((0, 0, 1), (1, 0, 3), (0, 5, 4), (7, 13, 16), (64, 32, 0)):
+            dst_buf = np.full(nbytes + 128, 0xA5, dtype=np.uint8)
+            src = src_buf[so:so + nbytes]
+            _cabi.check(L.ai_host_copy(dst_buf[do:].ctypes.data, src.ctypes.data, nbytes, threads))
+            assert np.array_equal(dst_buf[do:do + nbytes], src), (nbytes, so, do, threads)
+            assert np.all(dst_buf[:do] == 0xA5) and np.all(dst_buf[do + nbytes:] == 0xA5), (nbytes, so, do, threads)
+    assert L.ai_host_copy(None, src_buf.ctypes.data, 8, 1) == 1                  # AI_ERR_INVALID
+    assert L.ai_host_copy(src_buf.ctypes.data, src_buf.ctypes.data, -1, 1) == 1
