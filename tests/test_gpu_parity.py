@@ -693,6 +693,9 @@ def test_oversized_leaf_count_is_an_error_not_a_crash():
 # ------------------------------------------------------------------ host-buffer entry point
 @pytest.mark.parametrize("name,n", [("approx__32o6-p1.19209289551e-06", (1 << 25) + 12345),
                                     ("approx__64o7-p2.22044604925e-14", (1 << 23) + 77),
+                                    ("approx__32o6-p1.19209289551e-06", 1 << 24),          # exactly two chunks
+                                    ("approx__32o6-p1.19209289551e-06", (1 << 23) - 1),    # one element short of a chunk
+                                    ("approx__64o7-p2.22044604925e-14", (1 << 17) + 1),    # just above the staging threshold
                                     ("approx__32o6-p1.19209289551e-06", 1000)])
 def test_eval_host_pipeline(name, n, monkeypatch):
     """ai_eval_host_*: chunked H2D / kernel / D2H; more chunks than pipeline slots.  Pageable numpy
